@@ -1,0 +1,416 @@
+// attn.cu — decode attention for sm_100a: one launch per layer does what the reference does with
+//   split (3 memcpy) + [Qwen3 q/k RMSNorm ×2] + RoPE ×2 + KV concat (4 memcpy, O(ctx) re-copy) + TinyFA flash-attn
+//   [ref: src/layer/Attention.h:71-112,156-163; src/engine/CacheManager.h:24-42;
+//    TT/Operation/OpNNLayerCuda.cuh:252-299 (norm), :412-440 (rope);
+//    TFA/mma/kernel.cuh:18-203, TFA/mma/softmax.cuh:67-131 (online softmax, base-2 exponent)]
+//
+// Why not the reference's shape: TinyFA launches one CTA per Q head with a 128-row Q tile of which one row is live
+// and re-reads K/V once per Q head.  Here a CTA owns (KV head, KV split): the G = Hq/Hkv query heads that share the
+// KV head are processed together so K/V are read once, the context is split across `nsplit` CTAs so the whole GPU
+// works on one token, and the last CTA of a KV head (atomic ticket) merges the split partials — no second launch.
+// The KV cache is a pre-allocated [max_ctx, Hkv, hd] buffer written in place at position *pos.
+//
+// Numerics: q·k and P·V accumulate in fp32 over bf16 inputs; rounding points of q/k (after norm, after RoPE) are the
+// reference's.  Probabilities stay fp32 (the reference rounds P to bf16 before P·V, TFA/mma/layout.cuh:88-97); the
+// oracle models the reference's rounding and the parity tests bound the difference.
+#include "ops.cuh"
+
+#include <algorithm>
+#include <mutex>
+
+namespace b200 {
+
+namespace {
+
+constexpr int kAttnThreads = 256;
+constexpr int kAttnWarps = 8;
+constexpr float kLog2e = 1.4426950408889634f;
+
+template <int HD>
+struct InvSqrtHd;
+template <>
+struct InvSqrtHd<64> {
+  static constexpr float value = 0.125f;
+};
+template <>
+struct InvSqrtHd<128> {
+  static constexpr float value = 0.08838834764831845f;
+};
+
+template <int HD, int G>
+__global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnDecodeParams p) {
+  constexpr int LPK = HD / 8;           // lanes per key row (16-byte pieces)
+  constexpr int KPW = 32 / LPK;         // keys per warp per iteration
+  constexpr int NSLOT = kAttnThreads / LPK;
+  constexpr int EPL = HD / 32;          // elements per lane when a warp owns one head vector
+  constexpr float kScale = InvSqrtHd<HD>::value * kLog2e;
+
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  float* q_s = reinterpret_cast<float*>(smem_raw);                        // [G][HD]
+  float* pv_red = q_s + G * HD;                                           // [8][G][HD]
+  float* ml = pv_red + kAttnWarps * G * HD;                               // [G][2]
+  __nv_bfloat16* knew_s = reinterpret_cast<__nv_bfloat16*>(ml + 2 * G);   // [HD]
+  __nv_bfloat16* vnew_s = knew_s + HD;                                    // [HD]
+  float* sc = reinterpret_cast<float*>(vnew_s + HD);                      // [G][chunk_cap]
+  __shared__ bool is_last;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int kvh = blockIdx.y, split = blockIdx.x;
+
+  pdl_trigger();
+  pdl_wait();
+
+  const bool append = (p.pos != nullptr);
+  const int pos = append ? *p.pos : p.fixed_len - 1;
+  const int L = pos + 1;
+  int chunk = (L + p.nsplit - 1) / p.nsplit;
+  chunk = max(chunk, p.min_chunk);
+  const int nact = (L + chunk - 1) / chunk;
+  if (split >= nact) return;
+  const int start = split * chunk;
+  const int end = min(L, start + chunk);
+  const int chunk_cap = max((p.max_ctx + p.nsplit - 1) / p.nsplit, p.min_chunk);
+
+  const int qdim = p.Hq * HD, kvdim = p.Hkv * HD;
+
+  // ---- q heads (and the new k/v) : optional per-head RMSNorm, then RoPE, with the reference's roundings
+  for (int h = warp; h < G + 1; h += kAttnWarps) {
+    const bool is_k = (h == G);
+    if (is_k && !append) break;
+    const __nv_bfloat16* src = is_k ? p.qkv + qdim + kvh * HD : p.qkv + (kvh * G + h) * HD;
+    const __nv_bfloat16* nw = is_k ? p.k_norm : p.q_norm;
+    float x[EPL];
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) x[j] = bf16_to_f(src[lane + 32 * j]);
+    if (nw != nullptr) {
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) ss += x[j] * x[j];
+      ss = warp_sum(ss);
+      const float inv = rsqrtf(ss / (float)HD + p.eps);
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) x[j] = round_bf16(x[j] * inv * bf16_to_f(nw[lane + 32 * j]));
+    }
+    if (p.rope != nullptr) {
+      const float* row = p.rope + (size_t)pos * HD * 2;
+#pragma unroll
+      for (int j = 0; j < EPL / 2; ++j) {
+        const int i = lane + 32 * j;  // index inside the first half
+        const float c = row[i * 2], s = row[i * 2 + 1];
+        const float x1 = x[j], x2 = x[j + EPL / 2];
+        x[j] = round_bf16(x1 * c - x2 * s);
+        x[j + EPL / 2] = round_bf16(x2 * c + x1 * s);
+      }
+    }
+    if (is_k) {
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) {
+        knew_s[lane + 32 * j] = f_to_bf16(x[j]);
+        vnew_s[lane + 32 * j] = p.qkv[qdim + kvdim + kvh * HD + lane + 32 * j];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) q_s[h * HD + lane + 32 * j] = x[j];
+    }
+  }
+  __syncthreads();
+
+  // the split that holds position `pos` appends the new K/V row to the cache
+  if (append && split == nact - 1 && tid < 2 * (HD / 8)) {
+    const int which = tid / (HD / 8), piece = tid % (HD / 8);
+    const uint4 v = reinterpret_cast<const uint4*>(which ? vnew_s : knew_s)[piece];
+    __nv_bfloat16* dst = (which ? p.vcache : p.kcache) + ((size_t)pos * p.Hkv + kvh) * HD;
+    reinterpret_cast<uint4*>(dst)[piece] = v;
+  }
+
+  // ---- scores: LPK lanes cooperate on one key row, all G query heads at once
+  {
+    const int sub = lane / LPK, part = lane % LPK;
+    float qf[G][8];
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) qf[g][e] = q_s[g * HD + part * 8 + e];
+    for (int j0 = start + warp * KPW; j0 < end; j0 += kAttnWarps * KPW) {
+      const int j = j0 + sub;
+      const bool valid = j < end;
+      uint4 kv = make_uint4(0, 0, 0, 0);
+      if (valid) {
+        if (append && j == pos)
+          kv = reinterpret_cast<const uint4*>(knew_s)[part];
+        else
+          kv = reinterpret_cast<const uint4*>(p.kcache + ((size_t)j * p.Hkv + kvh) * HD)[part];
+      }
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        float d = dot8(kv, qf[g], 0.f);
+#pragma unroll
+        for (int o = LPK / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        if (valid && part == 0) sc[g * chunk_cap + (j - start)] = d;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- softmax inside the split (base-2 exponent like the reference): warp g owns head g
+  const int nk = end - start;
+  for (int g = warp; g < G; g += kAttnWarps) {
+    float* s = sc + g * chunk_cap;
+    float m = -INFINITY;
+    for (int j = lane; j < nk; j += 32) m = fmaxf(m, s[j]);
+    m = warp_max(m);
+    const float m_scaled = m * kScale;
+    float l = 0.f;
+    for (int j = lane; j < nk; j += 32) {
+      const float e = exp2f(s[j] * kScale - m_scaled);
+      s[j] = e;
+      l += e;
+    }
+    l = warp_sum(l);
+    if (lane == 0) {
+      ml[g * 2] = m;
+      ml[g * 2 + 1] = l;
+    }
+  }
+  __syncthreads();
+
+  // ---- P·V: thread = (key slot, 16-byte piece of the V row); G×8 fp32 accumulators
+  {
+    const int slot = tid / LPK, part = tid % LPK;
+    float acc[G][8];
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[g][e] = 0.f;
+    for (int j = start + slot; j < end; j += NSLOT) {
+      uint4 vv;
+      if (append && j == pos)
+        vv = reinterpret_cast<const uint4*>(vnew_s)[part];
+      else
+        vv = reinterpret_cast<const uint4*>(p.vcache + ((size_t)j * p.Hkv + kvh) * HD)[part];
+      float vf[8];
+      unpack8(vv, vf);
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const float pj = sc[g * chunk_cap + (j - start)];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[g][e] = fmaf(pj, vf[e], acc[g][e]);
+      }
+    }
+    // reduce over the key slots that live in the same warp, then across warps through shared memory
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float v = acc[g][e];
+#pragma unroll
+        for (int o = LPK; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        acc[g][e] = v;
+      }
+    if (lane < LPK) {
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) pv_red[(warp * G + g) * HD + lane * 8 + e] = acc[g][e];
+    }
+  }
+  __syncthreads();
+
+  float* ws_base = p.ws + ((size_t)kvh * p.nsplit) * G * (HD + 2);
+  for (int idx = tid; idx < G * HD; idx += kAttnThreads) {
+    float o = 0.f;
+#pragma unroll
+    for (int w = 0; w < kAttnWarps; ++w) o += pv_red[w * G * HD + idx];
+    const int g = idx / HD, d = idx % HD;
+    if (nact == 1) {
+      const float l = ml[g * 2 + 1];
+      p.out[(kvh * G + g) * HD + d] = f_to_bf16(o * (l > 0.f ? 1.f / l : 0.f));
+    } else {
+      ws_base[((size_t)split * G + g) * (HD + 2) + d] = o;
+    }
+  }
+  if (nact == 1) return;
+  if (tid < G) {
+    ws_base[((size_t)split * G + tid) * (HD + 2) + HD] = ml[tid * 2];
+    ws_base[((size_t)split * G + tid) * (HD + 2) + HD + 1] = ml[tid * 2 + 1];
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int t = atomicAdd(&p.tickets[kvh], 1u);
+    is_last = (t == (unsigned int)nact - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+
+  // ---- merge the split partials (last CTA of this KV head)
+  for (int idx = tid; idx < G * HD; idx += kAttnThreads) {
+    const int g = idx / HD, d = idx % HD;
+    float M = -INFINITY;
+    for (int s = 0; s < nact; ++s) M = fmaxf(M, __ldcg(&ws_base[((size_t)s * G + g) * (HD + 2) + HD]));
+    float num = 0.f, den = 0.f;
+    for (int s = 0; s < nact; ++s) {
+      const float* r = &ws_base[((size_t)s * G + g) * (HD + 2)];
+      const float w = exp2f((__ldcg(&r[HD]) - M) * kScale);
+      num = fmaf(w, __ldcg(&r[d]), num);
+      den = fmaf(w, __ldcg(&r[HD + 1]), den);
+    }
+    p.out[(kvh * G + g) * HD + d] = f_to_bf16(num * (den > 0.f ? 1.f / den : 0.f));
+  }
+  if (tid == 0) p.tickets[kvh] = 0;
+}
+
+template <int HD, int G>
+size_t attn_decode_smem(int chunk_cap) {
+  return (size_t)(G * HD + kAttnWarps * G * HD + 2 * G) * 4 + 2 * HD * 2 + (size_t)G * chunk_cap * 4;
+}
+
+using AttnFn = void (*)(const AttnDecodeParams);
+
+template <int HD>
+AttnFn pick_attn(int G) {
+  switch (G) {
+    case 1: return attn_decode_kernel<HD, 1>;
+    case 2: return attn_decode_kernel<HD, 2>;
+    case 3: return attn_decode_kernel<HD, 3>;
+    case 4: return attn_decode_kernel<HD, 4>;
+    case 7: return attn_decode_kernel<HD, 7>;
+    case 8: return attn_decode_kernel<HD, 8>;
+  }
+  return nullptr;
+}
+
+// ------------------------------------------------------------------------------------------ general attention
+// One CTA per (q row, head, batch); keys in chunks of 128 with online softmax.  Correctness path (prefill-shaped
+// calls through b200_attn_bf16); the tensor-core prefill kernel is separate work.
+template <int HD>
+__global__ void __launch_bounds__(128) attn_general_kernel(__nv_bfloat16* __restrict__ o,
+                                                           const __nv_bfloat16* __restrict__ q,
+                                                           const __nv_bfloat16* __restrict__ k,
+                                                           const __nv_bfloat16* __restrict__ v, int Sq, int Skv, int Hq,
+                                                           int Hkv, int causal) {
+  constexpr float kScale = InvSqrtHd<HD>::value * kLog2e;
+  __shared__ float qs[HD];
+  __shared__ float ps[128];
+  __shared__ float red[4];
+  const int row = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int kvh = h / (Hq / Hkv);
+  const int tid = threadIdx.x;
+  const __nv_bfloat16* qp = q + (((size_t)b * Sq + row) * Hq + h) * HD;
+  for (int d = tid; d < HD; d += 128) qs[d] = bf16_to_f(qp[d]);
+  __syncthreads();
+  const int nkeys = causal ? min(Skv, row + 1) : Skv;
+  float m_run = -INFINITY, l_run = 0.f, acc = 0.f;  // thread d < HD owns output column d
+  for (int c0 = 0; c0 < nkeys; c0 += 128) {
+    const int j = c0 + tid;
+    float s = -INFINITY;
+    if (j < nkeys) {
+      const uint4* kp = reinterpret_cast<const uint4*>(k + (((size_t)b * Skv + j) * Hkv + kvh) * HD);
+      float d = 0.f;
+#pragma unroll
+      for (int piece = 0; piece < HD / 8; ++piece) {
+        float qf[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) qf[e] = qs[piece * 8 + e];
+        d = dot8(kp[piece], qf, d);
+      }
+      s = d;
+    }
+    float cm = warp_max(s);
+    if ((tid & 31) == 0) red[tid >> 5] = cm;
+    __syncthreads();
+    cm = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    __syncthreads();
+    const float m_new = fmaxf(m_run, cm);
+    const float corr = (m_run == -INFINITY) ? 0.f : exp2f((m_run - m_new) * kScale);
+    const float e = (j < nkeys) ? exp2f(s * kScale - m_new * kScale) : 0.f;
+    ps[tid] = e;
+    float cs = warp_sum(e);
+    if ((tid & 31) == 0) red[tid >> 5] = cs;
+    __syncthreads();
+    cs = red[0] + red[1] + red[2] + red[3];
+    l_run = l_run * corr + cs;
+    m_run = m_new;
+    if (tid < HD) {
+      acc *= corr;
+      const int n = min(128, nkeys - c0);
+      for (int jj = 0; jj < n; ++jj)
+        acc = fmaf(ps[jj], bf16_to_f(v[(((size_t)b * Skv + c0 + jj) * Hkv + kvh) * HD + tid]), acc);
+    }
+    __syncthreads();
+  }
+  if (tid < HD) o[(((size_t)b * Sq + row) * Hq + h) * HD + tid] = f_to_bf16(acc * (l_run > 0.f ? 1.f / l_run : 0.f));
+}
+
+}  // namespace
+
+int64_t attn_decode_ws_floats(int Hq, int Hkv, int hd, int nsplit) {
+  return (int64_t)Hkv * nsplit * (Hq / Hkv) * (hd + 2);
+}
+
+int attn_setup_attributes() {
+  static std::once_flag once;
+  static int rc = B200_OK;
+  std::call_once(once, [] {
+    const int gs[6] = {1, 2, 3, 4, 7, 8};
+    for (int g : gs) {
+      AttnFn fns[2] = {pick_attn<64>(g), pick_attn<128>(g)};
+      for (AttnFn f : fns) {
+        cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (e != cudaSuccess) {
+          set_error("cudaFuncSetAttribute(attn smem) failed: %s", cudaGetErrorString(e));
+          rc = B200_ERR_CUDA;
+          (void)cudaGetLastError();
+          return;
+        }
+      }
+    }
+  });
+  return rc;
+}
+
+int launch_attn_decode(const AttnDecodeParams& p, int hd, cudaStream_t st, bool pdl) {
+  B200_CHECK_ARG(hd == 64 || hd == 128, "attention: head_dim %d not built (64 and 128 are, like the reference)", hd);
+  B200_CHECK_ARG(p.Hkv > 0 && p.Hq % p.Hkv == 0, "attention: Hq=%d must be a multiple of Hkv=%d", p.Hq, p.Hkv);
+  const int G = p.Hq / p.Hkv;
+  AttnFn f = (hd == 64) ? pick_attn<64>(G) : pick_attn<128>(G);
+  if (!f) {
+    set_error("attention: group size Hq/Hkv=%d not built (1,2,3,4,7,8 are)", G);
+    return B200_ERR_UNSUPPORTED;
+  }
+  B200_CHECK_ARG(p.nsplit >= 1 && p.min_chunk >= 1 && p.max_ctx >= 1, "attention: bad split configuration");
+  const int chunk_cap = std::max((p.max_ctx + p.nsplit - 1) / p.nsplit, p.min_chunk);
+  size_t smem = (size_t)(G * hd + kAttnWarps * G * hd + 2 * G) * 4 + 2 * hd * 2 + (size_t)G * chunk_cap * 4;
+  B200_CHECK_ARG(smem <= 160 * 1024, "attention: context %d with %d splits needs %zu bytes of shared memory", p.max_ctx,
+                 p.nsplit, smem);
+  B200_CUDA(launch_pdl(f, dim3(p.nsplit, p.Hkv), dim3(kAttnThreads), smem, st, pdl, p));
+  return B200_OK;
+}
+
+int launch_attn_general(void* o, const void* q, const void* k, const void* v, int64_t B, int64_t Sq, int64_t Skv,
+                        int64_t Hq, int64_t Hkv, int64_t hd, int causal, cudaStream_t st) {
+  B200_CHECK_ARG(hd == 64 || hd == 128, "attention: head_dim %lld not built (64 and 128 are)", (long long)hd);
+  B200_CHECK_ARG(B > 0 && Sq > 0 && Skv > 0 && Hkv > 0 && Hq % Hkv == 0 && Hq < 65536 && B < 65536,
+                 "attention: bad shape");
+  dim3 grid((unsigned)Sq, (unsigned)Hq, (unsigned)B);
+  g_launches.fetch_add(1);
+  if (hd == 64)
+    attn_general_kernel<64><<<grid, 128, 0, st>>>((__nv_bfloat16*)o, (const __nv_bfloat16*)q, (const __nv_bfloat16*)k,
+                                                  (const __nv_bfloat16*)v, (int)Sq, (int)Skv, (int)Hq, (int)Hkv, causal);
+  else
+    attn_general_kernel<128><<<grid, 128, 0, st>>>((__nv_bfloat16*)o, (const __nv_bfloat16*)q, (const __nv_bfloat16*)k,
+                                                   (const __nv_bfloat16*)v, (int)Sq, (int)Skv, (int)Hq, (int)Hkv,
+                                                   causal);
+  B200_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+}  // namespace b200
+
+extern "C" int b200_attn_bf16(void* o, const void* q, const void* k, const void* v, int64_t B, int64_t Sq, int64_t Skv,
+                              int64_t Hq, int64_t Hkv, int64_t hd, int causal, void* stream) {
+  using namespace b200;
+  B200_CHECK_ARG(o && q && k && v, "attention: null pointer");
+  return launch_attn_general(o, q, k, v, B, Sq, Skv, Hq, Hkv, hd, causal, (cudaStream_t)stream);
+}

@@ -1,0 +1,479 @@
+// engine.cu — the whole per-token forward behind GPTModel::forward / GPTEngine::genNextToken as ONE CUDA graph.
+//   [ref: src/model/GPTModel.h:51-58 CausalLM::forward; src/layer/DecoderLayer.h:38-43; src/layer/Attention.h:71-112;
+//    src/layer/GatedMLP.h:37-41; src/engine/CacheManager.h:13-55; src/engine/GPTEngine.cpp:94-99,154-174;
+//    src/engine/Sampler.cpp:23-29]
+//
+// Reference: ≈20 launches/memcpys per layer + host-side allocator traffic per op, O(ctx) KV re-copy per step.
+// Here, per layer (5 launches, PDL-chained so weight streaming of launch i+1 overlaps the tail of launch i):
+//   1. qkv   = GEMV[RMSNorm(x) prologue, +bias epilogue]
+//   2. attn  = q/k-norm + RoPE + in-place KV append + split-KV attention + merge          (attn.cu)
+//   3. x     = GEMV[o_proj, residual epilogue]
+//   4. act   = GEMV[RMSNorm(x) prologue, merged gate|up, SiLU·mul epilogue]
+//   5. x     = GEMV[down_proj, residual epilogue]
+// plus embed (token gather + position bookkeeping), lm_head GEMV[final RMSNorm prologue] and argmax; the greedy token
+// feeds the next step on device, so the generate loop has no host synchronisation.
+//
+// HBM layout (all allocated once at create): KV cache [L][2][max_ctx][Hkv][hd] bf16; activations (hidden, qkv, attn,
+// act, logits) a few KB each and L2-resident; split-KV workspace; device scalars (position, token, counters).
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "gemv.cuh"
+#include "ops.cuh"
+
+struct b200_engine {
+  b200_model_desc d{};
+  int num_sms = 148;
+  int qdim = 0, kvdim = 0, Hq_l = 0, Hkv_l = 0, I_l = 0, V_l = 0;  // local (per-rank) sizes
+  // borrowed weights
+  const __nv_bfloat16* embed = nullptr;
+  const float* rope = nullptr;
+  std::vector<b200_layer_weights> lw;
+  // owned device memory
+  uint8_t* arena = nullptr;
+  size_t arena_bytes = 0;
+  __nv_bfloat16 *kcache = nullptr, *vcache = nullptr;  // [L][max_ctx][Hkv_l][hd] each
+  __nv_bfloat16 *x = nullptr, *qkv = nullptr, *attn = nullptr, *act = nullptr, *logits = nullptr;
+  float* attn_ws = nullptr;
+  unsigned int* attn_tickets = nullptr;
+  void* argmax_ws = nullptr;
+  int64_t* cur_tok = nullptr;   // token the next step consumes
+  int64_t* gen_log = nullptr;   // ring of generated tokens
+  int* pos_next = nullptr;      // position the next token will occupy
+  int* pos_cur = nullptr;       // position of the token in flight (read by attention)
+  unsigned long long* gen_count = nullptr;
+  int gen_cap = 0;
+  int nsplit = 1;
+  // plans
+  std::vector<b200::GemvPlan> p_qkv, p_o, p_gu, p_down;
+  b200::GemvPlan p_head{};
+  // graphs
+  cudaGraphExec_t g_step = nullptr;   // full token incl. lm_head + argmax
+  cudaGraphExec_t g_body = nullptr;   // embed + layers only (prefill tokens whose logits nobody reads)
+  // host mirrors
+  int64_t h_pos = 0;
+  int64_t h_gen = 0;
+  int launches_per_token = 0;
+  bool use_graph = true;
+  bool use_pdl = true;
+};
+
+namespace b200 {
+
+namespace {
+
+// embed: x = E[cur_tok]; pos_cur = pos_next++   (first kernel of every token)
+__global__ void __launch_bounds__(128) embed_step_kernel(__nv_bfloat16* __restrict__ x,
+                                                         const __nv_bfloat16* __restrict__ table,
+                                                         const int64_t* __restrict__ tok, int64_t V, int H,
+                                                         int* pos_next, int* pos_cur) {
+  pdl_trigger();
+  pdl_wait();
+  int64_t id = *tok;
+  if (id < 0 || id >= V) id = 0;
+  const uint4* s4 = reinterpret_cast<const uint4*>(table + id * H);
+  uint4* d4 = reinterpret_cast<uint4*>(x);
+  for (int i = threadIdx.x; i < (H >> 3); i += blockDim.x) d4[i] = s4[i];
+  if (threadIdx.x == 0) {
+    const int p = *pos_next;
+    *pos_cur = p;
+    *pos_next = p + 1;
+  }
+}
+
+// after argmax: publish the greedy token as the next input and log it
+__global__ void publish_token_kernel(const int64_t* __restrict__ argmax_out, int64_t* cur_tok, int64_t* gen_log,
+                                     unsigned long long* gen_count, int gen_cap) {
+  pdl_trigger();
+  pdl_wait();
+  const int64_t t = *argmax_out;
+  *cur_tok = t;
+  const unsigned long long c = *gen_count;
+  gen_log[c % (unsigned long long)gen_cap] = t;
+  *gen_count = c + 1;
+}
+
+}  // namespace
+
+static int engine_launch_token(b200_engine* e, cudaStream_t st, bool with_head) {
+  const b200_model_desc& d = e->d;
+  const bool pdl = e->use_pdl;
+  int rc;
+  B200_CUDA(launch_pdl(embed_step_kernel, dim3(1), dim3(128), 0, st, pdl, e->x, e->embed, (const int64_t*)e->cur_tok,
+                       (int64_t)d.vocab, (int)d.hidden, e->pos_next, e->pos_cur));
+  const size_t kv_layer = (size_t)d.max_ctx * e->Hkv_l * d.head_dim;
+  for (int l = 0; l < d.layers; ++l) {
+    if ((rc = gemv_launch(e->p_qkv[l], st, pdl)) != B200_OK) return rc;
+    AttnDecodeParams a{};
+    a.qkv = e->qkv;
+    a.q_norm = (const __nv_bfloat16*)e->lw[l].q_norm;
+    a.k_norm = (const __nv_bfloat16*)e->lw[l].k_norm;
+    a.eps = d.rms_eps;
+    a.rope = e->rope;
+    a.pos = e->pos_cur;
+    a.fixed_len = 0;
+    a.kcache = e->kcache + (size_t)l * kv_layer;
+    a.vcache = e->vcache + (size_t)l * kv_layer;
+    a.out = e->attn;
+    a.ws = e->attn_ws;
+    a.tickets = e->attn_tickets;
+    a.Hq = e->Hq_l;
+    a.Hkv = e->Hkv_l;
+    a.nsplit = e->nsplit;
+    a.max_ctx = d.max_ctx;
+    a.min_chunk = 16;
+    if ((rc = launch_attn_decode(a, d.head_dim, st, pdl)) != B200_OK) return rc;
+    if ((rc = gemv_launch(e->p_o[l], st, pdl)) != B200_OK) return rc;
+    if ((rc = gemv_launch(e->p_gu[l], st, pdl)) != B200_OK) return rc;
+    if ((rc = gemv_launch(e->p_down[l], st, pdl)) != B200_OK) return rc;
+  }
+  if (with_head) {
+    if ((rc = gemv_launch(e->p_head, st, pdl)) != B200_OK) return rc;
+    int64_t* amax = reinterpret_cast<int64_t*>((uint8_t*)e->argmax_ws + argmax_workspace_bytes(1, e->V_l));
+    if ((rc = launch_argmax(amax, e->logits, 1, e->V_l, e->argmax_ws, st, pdl)) != B200_OK) return rc;
+    B200_CUDA(launch_pdl(publish_token_kernel, dim3(1), dim3(1), 0, st, pdl, (const int64_t*)amax, e->cur_tok,
+                         e->gen_log, e->gen_count, e->gen_cap));
+  }
+  return B200_OK;
+}
+
+static int engine_capture(b200_engine* e, bool with_head, cudaGraphExec_t* out) {
+  cudaStream_t st;
+  B200_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  cudaGraph_t g = nullptr;
+  cudaError_t err = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+  if (err != cudaSuccess) {
+    cudaStreamDestroy(st);
+    set_error("cudaStreamBeginCapture failed: %s", cudaGetErrorString(err));
+    return B200_ERR_CUDA;
+  }
+  const int64_t before = g_launches.load();
+  int rc = engine_launch_token(e, st, with_head);
+  const int64_t n = g_launches.load() - before;
+  g_launches.fetch_sub(n);  // capture does not execute anything
+  err = cudaStreamEndCapture(st, &g);
+  if (rc != B200_OK || err != cudaSuccess) {
+    if (g) cudaGraphDestroy(g);
+    cudaStreamDestroy(st);
+    if (rc == B200_OK) {
+      set_error("cudaStreamEndCapture failed: %s", cudaGetErrorString(err));
+      rc = B200_ERR_CUDA;
+    }
+    return rc;
+  }
+  if (with_head) e->launches_per_token = (int)n;
+  err = cudaGraphInstantiate(out, g, 0);
+  cudaGraphDestroy(g);
+  cudaStreamDestroy(st);
+  if (err != cudaSuccess) {
+    set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(err));
+    return B200_ERR_CUDA;
+  }
+  return B200_OK;
+}
+
+static int engine_run_token(b200_engine* e, cudaStream_t st, bool with_head) {
+  if (e->use_graph) {
+    cudaGraphExec_t g = with_head ? e->g_step : e->g_body;
+    B200_CUDA(cudaGraphLaunch(g, st));
+    g_launches.fetch_add(with_head ? e->launches_per_token : e->launches_per_token - 3);
+    return B200_OK;
+  }
+  return engine_launch_token(e, st, with_head);
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int engine_build(const b200_model_desc* desc, const b200_weight_table* w, b200_engine** out) {
+  B200_CHECK_ARG(desc && w && out, "engine_create: null argument");
+  *out = nullptr;
+  int rc = b200_device_check();
+  if (rc != B200_OK) return rc;
+  const b200_model_desc& d = *desc;
+  B200_CHECK_ARG(d.hidden > 0 && d.layers > 0 && d.q_heads > 0 && d.kv_heads > 0 && d.intermediate > 0 && d.vocab > 0 &&
+                     d.max_ctx > 0,
+                 "engine_create: non-positive model dimension");
+  B200_CHECK_ARG(d.head_dim == 64 || d.head_dim == 128, "engine_create: head_dim %d not built (64, 128)", d.head_dim);
+  B200_CHECK_ARG(d.q_heads % d.kv_heads == 0, "engine_create: q_heads %% kv_heads != 0");
+  B200_CHECK_ARG(d.hidden % 8 == 0 && d.intermediate % 8 == 0, "engine_create: H and I must be multiples of 8");
+  B200_CHECK_ARG(d.tp_world <= 1, "engine_create: use b200_engine_create_tp for tensor-parallel engines");
+  B200_CHECK_ARG(w->embed && w->final_norm && w->lm_head && w->rope_table && w->layers_host,
+                 "engine_create: null weight pointer");
+
+  b200_engine* e = new (std::nothrow) b200_engine();
+  if (!e) {
+    set_error("engine_create: out of host memory");
+    return B200_ERR_INVALID;
+  }
+  struct Guard {
+    b200_engine* e;
+    ~Guard() {
+      if (e) b200_engine_destroy(e);
+    }
+  } guard{e};
+
+  e->d = d;
+  e->d.tp_world = 1;
+  e->d.tp_rank = 0;
+  e->Hq_l = d.q_heads;
+  e->Hkv_l = d.kv_heads;
+  e->I_l = d.intermediate;
+  e->V_l = d.vocab;
+  e->qdim = e->Hq_l * d.head_dim;
+  e->kvdim = e->Hkv_l * d.head_dim;
+  e->embed = (const __nv_bfloat16*)w->embed;
+  e->rope = w->rope_table;
+  e->lw.assign(w->layers_host, w->layers_host + d.layers);
+  for (int l = 0; l < d.layers; ++l) {
+    const b200_layer_weights& lw = e->lw[l];
+    B200_CHECK_ARG(lw.input_norm && lw.qkv_w && lw.o_w && lw.post_norm && lw.gate_up_w && lw.down_w,
+                   "engine_create: layer %d has a null weight", l);
+    B200_CHECK_ARG(!d.qkv_bias || lw.qkv_b, "engine_create: layer %d: qkv_bias set but qkv_b is null", l);
+    B200_CHECK_ARG(!d.qk_norm || (lw.q_norm && lw.k_norm), "engine_create: layer %d: qk_norm set but norms null", l);
+  }
+  const char* env = std::getenv("B200_NO_GRAPH");
+  e->use_graph = !(env && env[0] == '1');
+  env = std::getenv("B200_NO_PDL");
+  e->use_pdl = !(env && env[0] == '1');
+
+  int dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  B200_CUDA(cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, dev));
+  B200_CUDA(cudaDeviceSynchronize());  // weights may still be in flight on the loader's stream
+  if ((rc = gemv_setup_attributes()) != B200_OK) return rc;
+  if ((rc = attn_setup_attributes()) != B200_OK) return rc;
+
+  // split-KV: enough CTAs to cover the GPU, at least 16 keys per split
+  e->nsplit = std::max(1, std::min(32, (e->num_sms + e->Hkv_l - 1) / e->Hkv_l));
+  env = std::getenv("B200_ATTN_NSPLIT");
+  if (env) e->nsplit = std::max(1, std::min(64, std::atoi(env)));
+  e->gen_cap = 1 << 16;
+
+  // ---- one arena for everything the engine owns
+  const size_t kv_bytes = (size_t)d.layers * d.max_ctx * e->kvdim * 2;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  };
+  const size_t o_k = take(kv_bytes), o_v = take(kv_bytes);
+  const size_t o_x = take((size_t)d.hidden * 2);
+  const size_t o_qkv = take((size_t)(e->qdim + 2 * e->kvdim) * 2);
+  const size_t o_attn = take((size_t)e->qdim * 2);
+  const size_t o_act = take((size_t)e->I_l * 2);
+  const size_t o_logits = take((size_t)e->V_l * 2);
+  const size_t o_ws = take((size_t)attn_decode_ws_floats(e->Hq_l, e->Hkv_l, d.head_dim, e->nsplit) * 4);
+  const size_t o_tick = take((size_t)e->Hkv_l * 4);
+  const size_t o_amax = take((size_t)argmax_workspace_bytes(1, e->V_l) + 16);
+  const size_t o_tok = take(8);
+  const size_t o_log = take((size_t)e->gen_cap * 8);
+  const size_t o_pos = take(16);
+  const size_t o_cnt = take(8);
+  e->arena_bytes = off;
+  B200_CUDA(cudaMalloc((void**)&e->arena, e->arena_bytes));
+  // zero only the small control region + activations (the KV cache is always written before it is read)
+  B200_CUDA(cudaMemset(e->arena + o_x, 0, e->arena_bytes - o_x));
+  e->kcache = (__nv_bfloat16*)(e->arena + o_k);
+  e->vcache = (__nv_bfloat16*)(e->arena + o_v);
+  e->x = (__nv_bfloat16*)(e->arena + o_x);
+  e->qkv = (__nv_bfloat16*)(e->arena + o_qkv);
+  e->attn = (__nv_bfloat16*)(e->arena + o_attn);
+  e->act = (__nv_bfloat16*)(e->arena + o_act);
+  e->logits = (__nv_bfloat16*)(e->arena + o_logits);
+  e->attn_ws = (float*)(e->arena + o_ws);
+  e->attn_tickets = (unsigned int*)(e->arena + o_tick);
+  e->argmax_ws = (void*)(e->arena + o_amax);
+  e->cur_tok = (int64_t*)(e->arena + o_tok);
+  e->gen_log = (int64_t*)(e->arena + o_log);
+  e->pos_next = (int*)(e->arena + o_pos);
+  e->pos_cur = e->pos_next + 1;
+  e->gen_count = (unsigned long long*)(e->arena + o_cnt);
+
+  // ---- GEMV plans (TMA descriptors are encoded once, here)
+  e->p_qkv.resize(d.layers);
+  e->p_o.resize(d.layers);
+  e->p_gu.resize(d.layers);
+  e->p_down.resize(d.layers);
+  const int nqkv = e->qdim + 2 * e->kvdim;
+  for (int l = 0; l < d.layers; ++l) {
+    const b200_layer_weights& lw = e->lw[l];
+    GemvPlan& q = e->p_qkv[l];
+    if ((rc = gemv_make_plan(&q, lw.qkv_w, nqkv, nqkv, d.hidden, 1, PRO_RMSNORM, EPI_PLAIN, e->num_sms)) != B200_OK)
+      return rc;
+    q.p.x = e->x;
+    q.p.norm_w = (const __nv_bfloat16*)lw.input_norm;
+    q.p.eps = d.rms_eps;
+    q.p.bias = d.qkv_bias ? (const __nv_bfloat16*)lw.qkv_b : nullptr;
+    q.p.y = e->qkv;
+
+    GemvPlan& o = e->p_o[l];
+    if ((rc = gemv_make_plan(&o, lw.o_w, d.hidden, d.hidden, e->qdim, 1, PRO_PLAIN, EPI_RESIDUAL, e->num_sms)) !=
+        B200_OK)
+      return rc;
+    o.p.x = e->attn;
+    o.p.residual = e->x;
+    o.p.y = e->x;
+
+    GemvPlan& g = e->p_gu[l];
+    if ((rc = gemv_make_plan(&g, lw.gate_up_w, 2 * (int64_t)e->I_l, e->I_l, d.hidden, 2, PRO_RMSNORM, EPI_SILU_MUL,
+                             e->num_sms)) != B200_OK)
+      return rc;
+    g.p.x = e->x;
+    g.p.norm_w = (const __nv_bfloat16*)lw.post_norm;
+    g.p.eps = d.rms_eps;
+    g.p.y = e->act;
+
+    GemvPlan& dn = e->p_down[l];
+    if ((rc = gemv_make_plan(&dn, lw.down_w, d.hidden, d.hidden, e->I_l, 1, PRO_PLAIN, EPI_RESIDUAL, e->num_sms)) !=
+        B200_OK)
+      return rc;
+    dn.p.x = e->act;
+    dn.p.residual = e->x;
+    dn.p.y = e->x;
+  }
+  if ((rc = gemv_make_plan(&e->p_head, w->lm_head, e->V_l, e->V_l, d.hidden, 1, PRO_RMSNORM, EPI_PLAIN, e->num_sms)) !=
+      B200_OK)
+    return rc;
+  e->p_head.p.x = e->x;
+  e->p_head.p.norm_w = (const __nv_bfloat16*)w->final_norm;
+  e->p_head.p.eps = d.rms_eps;
+  e->p_head.p.y = e->logits;
+
+  e->launches_per_token = 1 + 5 * d.layers + 3;
+  if (e->use_graph) {
+    if ((rc = engine_capture(e, true, &e->g_step)) != B200_OK) return rc;
+    if ((rc = engine_capture(e, false, &e->g_body)) != B200_OK) return rc;
+  }
+  guard.e = nullptr;
+  *out = e;
+  return B200_OK;
+}
+
+}  // namespace b200
+
+// --------------------------------------------------------------------------------------------------------- C ABI
+extern "C" {
+
+int b200_engine_create(const b200_model_desc* desc, const b200_weight_table* weights, b200_engine** out) {
+  return b200::engine_build(desc, weights, out);
+}
+
+void b200_engine_destroy(b200_engine* e) {
+  if (!e) return;
+  if (e->g_step) cudaGraphExecDestroy(e->g_step);
+  if (e->g_body) cudaGraphExecDestroy(e->g_body);
+  if (e->arena) cudaFree(e->arena);
+  delete e;
+}
+
+int b200_engine_reset(b200_engine* e, void* stream) {
+  using namespace b200;
+  B200_CHECK_ARG(e, "engine_reset: null engine");
+  B200_CUDA(cudaMemsetAsync(e->pos_next, 0, 16, (cudaStream_t)stream));
+  e->h_pos = 0;
+  return B200_OK;
+}
+
+int b200_engine_seek(b200_engine* e, int64_t position, void* stream) {
+  using namespace b200;
+  B200_CHECK_ARG(e, "engine_seek: null engine");
+  if (position < 0 || position > e->h_pos) {
+    set_error("engine_seek: position %lld is not inside the cached prefix [0, %lld]", (long long)position,
+              (long long)e->h_pos);
+    return B200_ERR_STATE;
+  }
+  const int v[2] = {(int)position, (int)position};
+  // small enough to travel in the command stream; stream-ordered with the graphs that read it
+  B200_CUDA(cudaMemcpyAsync(e->pos_next, v, 8, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  e->h_pos = position;
+  return B200_OK;
+}
+
+int b200_engine_forward(b200_engine* e, const int64_t* ids, int64_t B, int64_t S, void* logits_out, int logits_mode,
+                        void* stream) {
+  using namespace b200;
+  B200_CHECK_ARG(e && ids, "engine_forward: null argument");
+  B200_CHECK_ARG(B == 1, "engine_forward: batch %lld not built (decode engine is batch-1; run sequences one by one)",
+                 (long long)B);
+  B200_CHECK_ARG(S >= 1, "engine_forward: empty sequence");
+  B200_CHECK_ARG(logits_mode == 0 || logits_mode == 1, "engine_forward: logits_mode must be 0 or 1");
+  if (e->h_pos + S > e->d.max_ctx) {
+    set_error("engine_forward: position %lld + %lld tokens exceeds max_ctx %d", (long long)e->h_pos, (long long)S,
+              e->d.max_ctx);
+    return B200_ERR_STATE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t vbytes = (size_t)e->V_l * 2;
+  for (int64_t t = 0; t < S; ++t) {
+    B200_CUDA(cudaMemcpyAsync(e->cur_tok, ids + t, 8, cudaMemcpyDeviceToDevice, st));
+    const bool head = (t == S - 1) || (logits_mode == 1 && logits_out != nullptr);
+    int rc = engine_run_token(e, st, head);
+    if (rc != B200_OK) return rc;
+    if (head && logits_out != nullptr) {
+      uint8_t* dst = (uint8_t*)logits_out + (logits_mode == 1 ? (size_t)t * vbytes : 0);
+      B200_CUDA(cudaMemcpyAsync(dst, e->logits, vbytes, cudaMemcpyDeviceToDevice, st));
+    }
+    if (head) e->h_gen += 1;
+  }
+  e->h_pos += S;
+  return B200_OK;
+}
+
+int b200_engine_decode(b200_engine* e, int64_t n_steps, int64_t* tokens_out, void* stream) {
+  using namespace b200;
+  B200_CHECK_ARG(e && n_steps >= 0, "engine_decode: bad argument");
+  B200_CHECK_ARG(n_steps <= e->gen_cap, "engine_decode: at most %d steps per call", e->gen_cap);
+  if (e->h_pos + n_steps > e->d.max_ctx) {
+    set_error("engine_decode: position %lld + %lld steps exceeds max_ctx %d", (long long)e->h_pos, (long long)n_steps,
+              e->d.max_ctx);
+    return B200_ERR_STATE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t first = e->h_gen;
+  for (int64_t i = 0; i < n_steps; ++i) {
+    int rc = engine_run_token(e, st, true);
+    if (rc != B200_OK) return rc;
+  }
+  e->h_gen += n_steps;
+  e->h_pos += n_steps;
+  if (tokens_out != nullptr && n_steps > 0) {
+    const int64_t a = first % e->gen_cap;
+    const int64_t n1 = std::min<int64_t>(n_steps, e->gen_cap - a);
+    B200_CUDA(cudaMemcpyAsync(tokens_out, e->gen_log + a, (size_t)n1 * 8, cudaMemcpyDeviceToDevice, st));
+    if (n1 < n_steps)
+      B200_CUDA(cudaMemcpyAsync(tokens_out + n1, e->gen_log, (size_t)(n_steps - n1) * 8, cudaMemcpyDeviceToDevice, st));
+  }
+  return B200_OK;
+}
+
+int b200_engine_last_token(b200_engine* e, int64_t* token_out, void* stream) {
+  using namespace b200;
+  B200_CHECK_ARG(e && token_out, "engine_last_token: null argument");
+  B200_CUDA(cudaMemcpyAsync(token_out, e->cur_tok, 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return B200_OK;
+}
+
+int64_t b200_engine_position(const b200_engine* e) { return e ? e->h_pos : -1; }
+int64_t b200_engine_launches_per_token(const b200_engine* e) { return e ? e->launches_per_token : -1; }
+
+int64_t b200_engine_bytes_per_token(const b200_engine* e, int64_t ctx) {
+  if (!e) return -1;
+  const b200_model_desc& d = e->d;
+  const int64_t per_layer = (int64_t)(e->qdim + 2 * e->kvdim) * d.hidden + (int64_t)e->qdim * d.hidden +
+                            3ll * e->I_l * d.hidden;
+  const int64_t weights = 2 * ((int64_t)d.layers * per_layer + (int64_t)e->V_l * d.hidden);
+  const int64_t kv = 4ll * d.layers * e->kvdim * ctx + 4ll * d.layers * e->kvdim;
+  return weights + kv;
+}
+
+}  // extern "C"
+
+extern "C" int b200_engine_create_tp(const b200_model_desc* desc, const b200_weight_table* weights,
+                                     void* const* windows_host, b200_engine** out) {
+  (void)desc; (void)weights; (void)windows_host;
+  if (out) *out = nullptr;
+  b200::set_error("engine_create_tp: tensor-parallel engine not built yet");
+  return B200_ERR_UNSUPPORTED;
+}

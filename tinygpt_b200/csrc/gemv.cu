@@ -1,0 +1,367 @@
+// gemv.cu — the weight-bound bf16 GEMV that dominates batch-1 decode, written for sm_100a.
+//
+// Replaces, for m = 1:  Linear::forward → op::matmul(x, W, false, true, bias) → cublasGemmStridedBatchedEx
+//   [ref: third_party/TinyTorch/src/Operation/OpLinalg.cpp:244-277, OpLinalgCuda.cuh:276-293]
+// and fuses what the reference runs as separate launches around it:
+//   RMSNorm prologue      [ref: TT/Operation/OpNNLayerCuda.cuh:252-357]
+//   bias add epilogue     [ref: TT/Operation/OpLinalg.cpp:273-275 → OpElemWiseCuda.cuh:395-405]   (second rounding kept)
+//   residual add epilogue [ref: src/layer/DecoderLayer.h:38-43 → TT/Operation/OpElemWiseCuda.cuh:133-144]
+//   SiLU·mul epilogue     [ref: TT/Operation/OpFusedCuda.cuh:15-29, OpElemWiseCuda.cuh:124-131]   (both roundings kept)
+//
+// Design (HBM-bound: 2 bytes of W per FMA, so the only goal is to keep HBM saturated):
+//   * W[n,k] row-major is cut into boxes of (8·RPW rows) × (256 columns) = RPW·4 KB.  One elected producer thread
+//     streams the boxes of this CTA's row blocks with TMA (cp.async.bulk.tensor.2d → SASS UTMALDG) into a ring of
+//     `stages` shared-memory slots guarded by full/empty mbarriers; no registers are spent on loads in flight and
+//     ~80 KB per SM stay outstanding.
+//   * 8 consumer warps: warp w owns rows w·RPW … w·RPW+RPW-1 of the box; a lane reads one 16-byte vector of x and
+//     RPW 16-byte vectors of W per box (conflict-free: 32 lanes × 16 B = one 512-byte row), 8 FMAs each, fp32
+//     accumulators carried across the k loop; one xor-shuffle tree per row at the end.
+//   * Programmatic dependent launch: barrier init and the first `stages` TMA boxes are issued BEFORE
+//     griddepcontrol.wait — weights do not depend on the previous kernel — so the HBM stream of kernel i+1 starts
+//     while kernel i drains.  Only the activation vector is read after the wait.
+//   * grid = min(row blocks, #SMs) persistent CTAs, row blocks dealt round-robin.
+#include "gemv.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <mutex>
+
+namespace b200 {
+
+namespace {
+
+constexpr int kNW = 8;                      // consumer warps
+constexpr int kThreads = (kNW + 1) * 32;    // + 1 producer warp
+constexpr int kBoxK = 256;                  // columns per TMA box
+constexpr int kRowBytes = kBoxK * 2;        // 512
+constexpr int kConsumers = kNW * 32;
+constexpr int kSmemBudget = 100 * 1024;     // ≤ half an SM so that two PDL-overlapped kernels co-reside
+constexpr int kMaxStages = 32;
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_sys_add(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+template <int RPW, int NSEG, int PRO, int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap) {
+  constexpr int kBoxR = kNW * RPW;
+  constexpr int kStageBytes = NSEG * kBoxR * kRowBytes;
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* const stage_base = smem;
+  __nv_bfloat16* const xs = reinterpret_cast<__nv_bfloat16*>(smem + (size_t)p.stages * kStageBytes);
+  uint64_t* const full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xs) + (size_t)p.k_pad * 2);
+  uint64_t* const empty = full + p.stages;
+  float* const red = reinterpret_cast<float*>(empty + p.stages);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int ksteps = p.k_pad / kBoxK;
+  const int my_rbs = (p.rowblocks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kNW);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_trigger();  // dependents only prefetch weights before their own griddepcontrol.wait
+
+  if (warp == kNW) {
+    // ------------------------------------------------------------------ producer: one thread drives the TMA ring
+    if (lane == 0) {
+      tma_prefetch_desc(&tmap);
+      int s = 0;
+      uint32_t ph = 1;  // first pass over the ring: slots are free (wait on the "previous" phase returns at once)
+      for (int i = 0; i < my_rbs; ++i) {
+        const int row0 = ((int)blockIdx.x + i * (int)gridDim.x) * kBoxR;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(&empty[s], ph);
+          mbar_arrive_expect_tx(&full[s], kStageBytes);
+          uint8_t* dst = stage_base + (size_t)s * kStageBytes;
+#pragma unroll
+          for (int seg = 0; seg < NSEG; ++seg)
+            tma_load_2d(dst + seg * kBoxR * kRowBytes, &tmap, ks * kBoxK, seg * p.seg_rows + row0, &full[s]);
+          if (++s == p.stages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- consumers: wait for the producer kernel
+  pdl_wait();
+  const int ctid = threadIdx.x;  // 0 … 255
+
+  if constexpr (PRO == PRO_PLAIN) {
+    const uint4* xg = reinterpret_cast<const uint4*>(p.x);
+    uint4* xv = reinterpret_cast<uint4*>(xs);
+    const int nvec = p.k >> 3, nvec_pad = p.k_pad >> 3;
+    for (int i = ctid; i < nvec_pad; i += kConsumers) xv[i] = (i < nvec) ? xg[i] : make_uint4(0, 0, 0, 0);
+  } else {
+    // hidden vector h (k elements): either x itself, or residual + Σ_r partial_r (tensor parallel)
+    const int nvec = p.k >> 3, nvec_pad = p.k_pad >> 3;
+    float ss = 0.f;
+    if constexpr (PRO == PRO_TP_RMSNORM) {
+      if (ctid == 0) {
+        const unsigned long long want = (*p.tp_epoch + 1ull) * (unsigned long long)p.tp_arrivals;
+        while (ld_acquire_sys(p.tp_wait_flag) < want) {
+        }
+      }
+      named_bar_sync(1, kConsumers);
+      // h = bf16(residual + bf16(Σ partial)), staged in xs as bf16 first
+      for (int i = ctid; i < p.k; i += kConsumers) {
+        float a = 0.f;
+        for (int r = 0; r < p.tp_world; ++r) a += __ldcv(p.tp_partials + (size_t)r * p.k + i);
+        const __nv_bfloat16 h = __hadd(p.tp_residual[i], f_to_bf16(a));
+        xs[i] = h;
+        if (blockIdx.x == 0) p.tp_h_out[i] = h;
+        const float hf = bf16_to_f(h);
+        ss += hf * hf;
+      }
+    } else {
+      const uint4* xg = reinterpret_cast<const uint4*>(p.x);
+      for (int i = ctid; i < nvec; i += kConsumers) {
+        float xf[8];
+        unpack8(xg[i], xf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss += xf[j] * xf[j];
+      }
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) red[warp] = ss;
+    named_bar_sync(1, kConsumers);
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < kNW; ++w) tot += red[w];
+    const float inv = rsqrtf(tot / (float)p.k + p.eps);
+    const uint4* wg = reinterpret_cast<const uint4*>(p.norm_w);
+    uint4* xv = reinterpret_cast<uint4*>(xs);
+    for (int i = ctid; i < nvec_pad; i += kConsumers) {
+      uint4 o = make_uint4(0, 0, 0, 0);
+      if (i < nvec) {
+        float xf[8], wf[8];
+        if constexpr (PRO == PRO_TP_RMSNORM) {
+          unpack8(xv[i], xf);
+        } else {
+          unpack8(reinterpret_cast<const uint4*>(p.x)[i], xf);
+        }
+        unpack8(wg[i], wf);
+        // reference order: normed = x * inv; normed *= w; round once
+        o.x = pack2(xf[0] * inv * wf[0], xf[1] * inv * wf[1]);
+        o.y = pack2(xf[2] * inv * wf[2], xf[3] * inv * wf[3]);
+        o.z = pack2(xf[4] * inv * wf[4], xf[5] * inv * wf[5]);
+        o.w = pack2(xf[6] * inv * wf[6], xf[7] * inv * wf[7]);
+      }
+      xv[i] = o;
+    }
+  }
+  named_bar_sync(1, kConsumers);
+
+  // ---------------------------------------------------------------------------------------------- main k loop
+  int s = 0;
+  uint32_t ph = 0;
+  const uint8_t* const my_rows = stage_base + (size_t)(warp * RPW) * kRowBytes + lane * 16;
+  for (int i = 0; i < my_rbs; ++i) {
+    float acc[NSEG][RPW];
+#pragma unroll
+    for (int seg = 0; seg < NSEG; ++seg)
+#pragma unroll
+      for (int r = 0; r < RPW; ++r) acc[seg][r] = 0.f;
+
+    for (int ks = 0; ks < ksteps; ++ks) {
+      const uint4 xvv = *reinterpret_cast<const uint4*>(xs + ks * kBoxK + lane * 8);
+      float xf[8];
+      unpack8(xvv, xf);
+      mbar_wait(&full[s], ph);
+      const uint8_t* st = my_rows + (size_t)s * kStageBytes;
+      uint4 wv[NSEG][RPW];
+#pragma unroll
+      for (int seg = 0; seg < NSEG; ++seg)
+#pragma unroll
+        for (int r = 0; r < RPW; ++r)
+          wv[seg][r] = *reinterpret_cast<const uint4*>(st + (seg * kBoxR + r) * kRowBytes);
+#pragma unroll
+      for (int seg = 0; seg < NSEG; ++seg)
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) acc[seg][r] = dot8(wv[seg][r], xf, acc[seg][r]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+      if (++s == p.stages) {
+        s = 0;
+        ph ^= 1;
+      }
+    }
+
+#pragma unroll
+    for (int seg = 0; seg < NSEG; ++seg)
+#pragma unroll
+      for (int r = 0; r < RPW; ++r) acc[seg][r] = warp_sum(acc[seg][r]);
+
+    const int row_base = ((int)blockIdx.x + i * (int)gridDim.x) * kBoxR + warp * RPW;
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const int row = row_base + r;
+      if (lane == r && row < p.n) {
+        if constexpr (EPI == EPI_PLAIN) {
+          __nv_bfloat16 v = f_to_bf16(acc[0][r]);
+          if (p.bias != nullptr) v = __hadd(v, p.bias[row]);
+          p.y[row] = v;
+        } else if constexpr (EPI == EPI_RESIDUAL) {
+          p.y[row] = __hadd(p.residual[row], f_to_bf16(acc[0][r]));
+        } else if constexpr (EPI == EPI_SILU_MUL) {
+          const float g = round_bf16(acc[0][r]);
+          const __nv_bfloat16 sg = f_to_bf16(g / (1.f + expf(-g)));
+          p.y[row] = __hmul(sg, f_to_bf16(acc[NSEG - 1][r]));
+        } else {  // EPI_TP_PUSH
+          for (int q = 0; q < p.tp_world; ++q) p.tp_push[q][row] = acc[0][r];
+        }
+      }
+    }
+  }
+
+  if constexpr (EPI == EPI_TP_PUSH) {
+    __threadfence_system();
+    named_bar_sync(1, kConsumers);
+    if (ctid < p.tp_world) red_release_sys_add(p.tp_flag[ctid], 1ull);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------ dispatch
+using KernelFn = void (*)(const GemvParams, const CUtensorMap);
+
+template <int RPW>
+KernelFn pick_kernel(int nseg, int pro, int epi) {
+  if (nseg == 2) {
+    if (epi != EPI_SILU_MUL) return nullptr;
+    switch (pro) {
+      case PRO_PLAIN: return gemv_stream_kernel<RPW, 2, PRO_PLAIN, EPI_SILU_MUL>;
+      case PRO_RMSNORM: return gemv_stream_kernel<RPW, 2, PRO_RMSNORM, EPI_SILU_MUL>;
+      case PRO_TP_RMSNORM: return gemv_stream_kernel<RPW, 2, PRO_TP_RMSNORM, EPI_SILU_MUL>;
+    }
+    return nullptr;
+  }
+#define B200_PICK(P, E) \
+  if (pro == P && epi == E) return gemv_stream_kernel<RPW, 1, P, E>;
+  B200_PICK(PRO_PLAIN, EPI_PLAIN)
+  B200_PICK(PRO_PLAIN, EPI_RESIDUAL)
+  B200_PICK(PRO_PLAIN, EPI_TP_PUSH)
+  B200_PICK(PRO_RMSNORM, EPI_PLAIN)
+  B200_PICK(PRO_TP_RMSNORM, EPI_PLAIN)
+#undef B200_PICK
+  return nullptr;
+}
+
+KernelFn pick(int rpw, int nseg, int pro, int epi) {
+  switch (rpw) {
+    case 1: return pick_kernel<1>(nseg, pro, epi);
+    case 2: return pick_kernel<2>(nseg, pro, epi);
+    case 4: return pick_kernel<4>(nseg, pro, epi);
+  }
+  return nullptr;
+}
+
+}  // namespace
+
+int gemv_setup_attributes() {
+  static std::once_flag once;
+  static int rc = B200_OK;
+  std::call_once(once, [] {
+    const int rpws[3] = {1, 2, 4};
+    for (int rpw : rpws)
+      for (int nseg = 1; nseg <= 2; ++nseg)
+        for (int pro = 0; pro < 3; ++pro)
+          for (int epi = 0; epi < 4; ++epi) {
+            KernelFn f = pick(rpw, nseg, pro, epi);
+            if (!f) continue;
+            cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 4096);
+            if (e != cudaSuccess) {
+              set_error("cudaFuncSetAttribute(gemv smem) failed: %s", cudaGetErrorString(e));
+              rc = B200_ERR_CUDA;
+              (void)cudaGetLastError();
+              return;
+            }
+          }
+  });
+  return rc;
+}
+
+int gemv_make_plan(GemvPlan* plan, const void* W, int64_t rows_total, int64_t n, int64_t k, int nseg, int pro, int epi,
+                   int num_sms) {
+  B200_CHECK_ARG(W != nullptr && n > 0 && k > 0, "gemv: null weight or empty shape (n=%lld k=%lld)", (long long)n,
+                 (long long)k);
+  B200_CHECK_ARG(k % 8 == 0, "gemv: k=%lld must be a multiple of 8 (16-byte rows)", (long long)k);
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(W) & 15) == 0, "gemv: W must be 16-byte aligned");
+  B200_CHECK_ARG(nseg == 1 || nseg == 2, "gemv: nseg must be 1 or 2");
+  B200_CHECK_ARG(n < (1ll << 30) && k < (1ll << 30) && rows_total >= n * nseg, "gemv: shape out of range");
+
+  // rows per warp: maximise the share of busy SM-slots, prefer bigger boxes when within 3 %
+  int best_rpw = 1;
+  double best_eff = -1.0;
+  const char* force = std::getenv("B200_GEMV_RPW");
+  const int cands[3] = {4, 2, 1};
+  for (int rpw : cands) {
+    if (force && std::atoi(force) != rpw) continue;
+    const int64_t rbs = (n + 8 * rpw - 1) / (8 * rpw);
+    const int64_t g = std::min<int64_t>(rbs, num_sms);
+    // time ∝ (row blocks of the busiest CTA) × rows per block; ideal = n / 8 / num_sms
+    const double eff = ((double)n / 8.0 / (double)num_sms) / (double)(((rbs + g - 1) / g) * rpw);
+    if (eff > best_eff + 0.03) {
+      best_eff = eff;
+      best_rpw = rpw;
+    }
+  }
+  const int rpw = best_rpw;
+  const int box_r = 8 * rpw;
+  const int64_t rbs = (n + box_r - 1) / box_r;
+  const int k_pad = (int)((k + kBoxK - 1) / kBoxK * kBoxK);
+  const int stage_bytes = nseg * box_r * kRowBytes;
+  const int fixed = k_pad * 2 + 64;  // x vector + reduction scratch
+  int stages = (kSmemBudget - fixed) / (stage_bytes + 16);
+  stages = std::max(2, std::min(stages, kMaxStages));
+  const char* fs = std::getenv("B200_GEMV_STAGES");
+  if (fs) stages = std::max(2, std::min(std::atoi(fs), kMaxStages));
+
+  *plan = GemvPlan{};
+  plan->rpw = rpw;
+  plan->nseg = nseg;
+  plan->pro = pro;
+  plan->epi = epi;
+  plan->grid = (int)std::min<int64_t>(rbs, num_sms);
+  plan->smem = stages * stage_bytes + k_pad * 2 + stages * 16 + 64;
+  plan->p.n = (int)n;
+  plan->p.k = (int)k;
+  plan->p.k_pad = k_pad;
+  plan->p.seg_rows = (nseg == 2) ? (int)n : 0;
+  plan->p.rowblocks = (int)rbs;
+  plan->p.stages = stages;
+  plan->p.tp_world = 1;
+  B200_CHECK_ARG(pick(rpw, nseg, pro, epi) != nullptr, "gemv: no kernel for nseg=%d pro=%d epi=%d", nseg, pro, epi);
+  B200_CHECK_ARG(plan->smem <= kSmemBudget + 4096, "gemv: k=%lld needs %d bytes of shared memory", (long long)k,
+                 plan->smem);
+  return make_tmap_2d_bf16(&plan->tmap, W, rows_total, k, box_r, kBoxK);
+}
+
+int gemv_launch(const GemvPlan& plan, cudaStream_t stream, bool pdl) {
+  KernelFn f = pick(plan.rpw, plan.nseg, plan.pro, plan.epi);
+  if (!f) {
+    set_error("gemv: no kernel instantiation");
+    return B200_ERR_INVALID;
+  }
+  B200_CUDA(launch_pdl(f, dim3(plan.grid), dim3(kThreads), (size_t)plan.smem, stream, pdl, plan.p, plan.tmap));
+  return B200_OK;
+}
+
+}  // namespace b200

@@ -1,0 +1,63 @@
+// gemv.cuh — host-side plan/launch interface of the weight-streaming bf16 GEMV (see gemv.cu).
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+// Prologue: how the activation vector x[k] gets into shared memory.
+//   PRO_PLAIN       x is read as is
+//   PRO_RMSNORM     x ← bf16(x * rsqrt(mean(x²)+eps) * w)              (fused input/post-attention/final RMSNorm)
+//   PRO_TP_RMSNORM  h ← bf16(residual + bf16(Σ_r partial_r)); x ← rmsnorm(h); CTA 0 stores h  (tensor parallel)
+enum GemvPro : int { PRO_PLAIN = 0, PRO_RMSNORM = 1, PRO_TP_RMSNORM = 2 };
+// Epilogue: what happens to the fp32 row sums.
+//   EPI_PLAIN     y = bf16(acc); with bias: y = bf16(y + bias)         (reference: second rounding, 3-D Linear input)
+//   EPI_RESIDUAL  y = bf16(residual + bf16(acc))                        (o_proj / down_proj + DecoderLayer add)
+//   EPI_SILU_MUL  y = bf16(bf16(silu(bf16(acc_gate))) * bf16(acc_up))   (merged gate|up projection + SiLUMul)
+//   EPI_TP_PUSH   fp32 acc stored into every tensor-parallel peer's exchange window + arrival flag
+enum GemvEpi : int { EPI_PLAIN = 0, EPI_RESIDUAL = 1, EPI_SILU_MUL = 2, EPI_TP_PUSH = 3 };
+
+constexpr int kMaxTpWorld = 8;
+
+struct GemvParams {
+  const __nv_bfloat16* x;         // [k] activation
+  const __nv_bfloat16* norm_w;    // [k] RMSNorm weight or null
+  float eps;
+  const __nv_bfloat16* bias;      // [n] or null
+  const __nv_bfloat16* residual;  // [n]; may alias y
+  __nv_bfloat16* y;               // [n]
+  int n;                          // output rows (per segment)
+  int k;                          // reduction length
+  int k_pad;                      // k rounded up to the 256-element TMA box
+  int seg_rows;                   // row offset of segment 1 inside W (NSEG == 2: gate rows | up rows)
+  int rowblocks;                  // ceil(n / (8 * RPW))
+  int stages;                     // depth of the shared-memory ring
+  // ---- tensor-parallel exchange (peer-mapped windows over NVLink), see tp.cuh
+  float* tp_push[kMaxTpWorld];            // EPI_TP_PUSH: slot for MY partial inside rank r's window ([n] floats)
+  unsigned long long* tp_flag[kMaxTpWorld];  // EPI_TP_PUSH: rank r's arrival counter for this exchange point
+  const float* tp_partials;               // PRO_TP_RMSNORM: local window, tp_world vectors of k floats
+  const unsigned long long* tp_wait_flag; // PRO_TP_RMSNORM: local arrival counter
+  const unsigned long long* tp_epoch;     // device counter: tokens completed (expected arrivals = (epoch+1)*tp_arrivals)
+  unsigned int tp_arrivals;               // arrivals per token at that exchange point (world × producer CTAs)
+  const __nv_bfloat16* tp_residual;       // PRO_TP_RMSNORM: hidden state before the add
+  __nv_bfloat16* tp_h_out;                // PRO_TP_RMSNORM: CTA 0 stores the new hidden state (≠ tp_residual)
+  int tp_world;
+};
+
+struct GemvPlan {
+  CUtensorMap tmap;
+  GemvParams p;
+  int rpw;   // rows per consumer warp: 1, 2 or 4
+  int nseg;  // 1, or 2 for merged gate|up
+  int pro;
+  int epi;
+  int grid;
+  int smem;
+};
+
+// Plan a GEMV over W[rows_total, k] (row-major bf16).  `n` = rows produced (per segment).
+int gemv_make_plan(GemvPlan* plan, const void* W, int64_t rows_total, int64_t n, int64_t k, int nseg, int pro, int epi,
+                   int num_sms);
+int gemv_launch(const GemvPlan& plan, cudaStream_t stream, bool pdl);
+int gemv_setup_attributes();  // cudaFuncSetAttribute(max dynamic smem) for every instantiation, once per process
+
+}  // namespace b200

@@ -1,0 +1,48 @@
+// ops.cuh — host launchers of the small decode-path operators (ops.cu) and of attention (attn.cu).
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+int launch_rmsnorm(void* y, const void* x, const void* w, int64_t rows, int64_t dim, float eps, cudaStream_t st,
+                   bool pdl);
+int launch_rope(void* y, const void* x, const float* table, int64_t B, int64_t S, int64_t heads, int64_t hd,
+                int64_t offset, int layout, cudaStream_t st, bool pdl);
+int launch_silu_mul(void* y, const void* gu, int64_t rows, int64_t I, cudaStream_t st, bool pdl);
+int launch_add(void* y, const void* a, const void* b, int64_t n, cudaStream_t st, bool pdl);
+int launch_embedding(void* y, const void* table, const int64_t* ids, int64_t n_ids, int64_t V, int64_t H,
+                     cudaStream_t st, bool pdl);
+int argmax_chunks(int64_t V);
+int64_t argmax_workspace_bytes(int64_t rows, int64_t V);
+int launch_argmax(int64_t* idx, const void* logits, int64_t rows, int64_t V, void* workspace, cudaStream_t st,
+                  bool pdl);
+
+// ---- attention (attn.cu)
+// Fused decode attention of one layer for one new token (B = 1, Sq = 1):
+//   q,k,v = split(qkv)  →  optional per-head RMSNorm on q,k (Qwen3)  →  RoPE(q), RoPE(k) at position *pos  →
+//   K/V appended in place to the cache  →  split-KV softmax(q kᵀ/√hd) v over positions 0…*pos  →  o (bf16).
+struct AttnDecodeParams {
+  const __nv_bfloat16* qkv;      // [Hq*hd + 2*Hkv*hd] projections (bias already applied)
+  const __nv_bfloat16* q_norm;   // [hd] or null
+  const __nv_bfloat16* k_norm;   // [hd] or null
+  float eps;
+  const float* rope;             // [max_ctx, hd, 2] fp32 table, or null (no rotation: stand-alone attention op)
+  const int* pos;                // device scalar: past length (index of the new token); null ⇒ fixed_len - 1
+  int fixed_len;                 // used when pos == null: number of keys, nothing is appended
+  __nv_bfloat16* kcache;         // [max_ctx, Hkv, hd]
+  __nv_bfloat16* vcache;         // [max_ctx, Hkv, hd]
+  __nv_bfloat16* out;            // [Hq*hd]
+  float* ws;                     // split partials: [Hkv][nsplit][G][hd + 2] floats
+  unsigned int* tickets;         // [Hkv], zero-initialised, self-resetting
+  int Hq, Hkv, nsplit, max_ctx;
+  int min_chunk;                 // keys per split at least this many
+};
+int launch_attn_decode(const AttnDecodeParams& p, int hd, cudaStream_t st, bool pdl);
+int64_t attn_decode_ws_floats(int Hq, int Hkv, int hd, int nsplit);
+int attn_setup_attributes();
+
+// General (any Sq, causal or not) attention — correctness path behind b200_attn_bf16 for Sq > 1.
+int launch_attn_general(void* o, const void* q, const void* k, const void* v, int64_t B, int64_t Sq, int64_t Skv,
+                        int64_t Hq, int64_t Hkv, int64_t hd, int causal, cudaStream_t st);
+
+}  // namespace b200

@@ -1,0 +1,151 @@
+"""Host-side mirror of tinygpt::GPTModel / GPTEngine for the greedy decode path, over the C-ABI engine.
+
+  DecodeEngine.forward(ids)      ↔ GPTModel::forward → model()(inputIds)            [ref: src/model/GPTModel.h:86]
+  DecodeEngine.reset_cache()     ↔ GPTModel::resetCache                             [ref: src/model/GPTModel.h:91-94]
+  DecodeEngine.gen_next_token()  ↔ GPTEngine::genNextToken (greedy sampler)         [ref: src/engine/GPTEngine.cpp:94-99]
+  DecodeEngine.generate_sync()   ↔ GPTEngine::generateSync, batch 1, greedy         [ref: src/engine/GPTEngine.cpp:154-174]
+
+torch is used for device memory, pinned host buffers and the current stream only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional
+
+import torch
+
+from . import models
+from ._lib import B200Error, LayerWeights, ModelDesc, WeightTable, check, lib, require_device
+
+
+class DecodeEngine:
+    """Whole-token engine for ONE sequence (batch 1) on the current CUDA device.
+
+    `weights` is a dict with the reference's merged layout (models.synth_weights) already on the device; the engine
+    borrows the tensors (keeps references) and owns only its KV cache + workspace."""
+
+    def __init__(self, spec: models.ModelSpec, weights: Dict[str, torch.Tensor], rope_table: Optional[torch.Tensor] = None):
+        require_device()
+        self.spec = spec
+        dev = weights["model.embed_tokens.weight"].device
+        if dev.type != "cuda":
+            raise B200Error("DecodeEngine: weights must be on a CUDA device (no CPU path)")
+        self.device = dev
+        self._w = weights  # keep alive
+        self._rope = (models.rope_table(spec) if rope_table is None else rope_table).to(dev).contiguous()
+        L = spec.layers
+        arr = (LayerWeights * L)()
+        for l in range(L):
+            p = f"model.layers.{l}."
+            g = lambda k: self._ptr(weights.get(p + k))
+            arr[l] = LayerWeights(g("input_layernorm.weight"), g("self_attn.qkv_proj.weight"),
+                                  g("self_attn.qkv_proj.bias"), g("self_attn.q_norm.weight"),
+                                  g("self_attn.k_norm.weight"), g("self_attn.o_proj.weight"),
+                                  g("post_attention_layernorm.weight"), g("mlp.gate_up_proj.weight"),
+                                  g("mlp.down_proj.weight"))
+        head = weights["model.embed_tokens.weight"] if spec.tie else weights["lm_head.weight"]
+        self._layers = arr
+        table = WeightTable(self._ptr(weights["model.embed_tokens.weight"]), self._ptr(weights["model.norm.weight"]),
+                            self._ptr(head), self._rope.data_ptr(), arr)
+        desc = ModelDesc(spec.hidden, L, spec.q_heads, spec.kv_heads, spec.head_dim, spec.intermediate, spec.vocab,
+                         spec.max_ctx, spec.rms_eps, int(spec.qkv_bias), int(spec.qk_norm), 0, 1, 1)
+        h = C.c_void_p()
+        with torch.cuda.device(dev):
+            check(lib().b200_engine_create(C.byref(desc), C.byref(table), C.byref(h)), "b200_engine_create")
+        self._h = h
+        self._tok_dev = torch.empty(1, dtype=torch.int64, device=dev)
+
+    @staticmethod
+    def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+        if t is None:
+            return None
+        if t.dtype != torch.bfloat16 or not t.is_contiguous():
+            raise B200Error("DecodeEngine: weights must be contiguous bf16 tensors")
+        return t.data_ptr()
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().b200_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------------ state
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    @property
+    def position(self) -> int:
+        return int(lib().b200_engine_position(self._h))
+
+    @property
+    def launches_per_token(self) -> int:
+        return int(lib().b200_engine_launches_per_token(self._h))
+
+    def bytes_per_token(self, ctx: int) -> int:
+        return int(lib().b200_engine_bytes_per_token(self._h, ctx))
+
+    def reset_cache(self) -> None:
+        check(lib().b200_engine_reset(self._h, self._stream()), "b200_engine_reset")
+
+    def seek(self, position: int) -> None:
+        """Rewind to `position` inside the cached prefix (rows below it stay valid)."""
+        check(lib().b200_engine_seek(self._h, int(position), self._stream()), "b200_engine_seek")
+
+    # ---------------------------------------------------------------------------------------------- forward
+    def forward(self, ids: torch.Tensor, all_positions: bool = False) -> torch.Tensor:
+        """ids [1, S] int64 on the device → logits [1, S, V] (all_positions) or [1, 1, V] (last position) bf16."""
+        if ids.dim() != 2 or ids.shape[0] != 1:
+            raise B200Error("DecodeEngine.forward: ids must be [1, S] (batch-1 engine)")
+        if ids.dtype != torch.int64 or not ids.is_cuda:
+            raise B200Error("DecodeEngine.forward: ids must be int64 on the device (reference: FuncNNLayer.h:205)")
+        ids = ids.contiguous()
+        S = ids.shape[1]
+        rows = S if all_positions else 1
+        logits = torch.empty(1, rows, self.spec.vocab, dtype=torch.bfloat16, device=self.device)
+        check(lib().b200_engine_forward(self._h, ids.data_ptr(), 1, S, logits.data_ptr(), int(all_positions),
+                                        self._stream()), "b200_engine_forward")
+        return logits
+
+    def gen_next_token(self, ids: torch.Tensor) -> torch.Tensor:
+        """genNextToken: forward → last position → greedy argmax (device tensor [1, 1] int64)."""
+        check(lib().b200_engine_forward(self._h, ids.contiguous().data_ptr(), 1, ids.shape[1], None, 0, self._stream()),
+              "b200_engine_forward")
+        out = torch.empty(1, 1, dtype=torch.int64, device=self.device)
+        check(lib().b200_engine_last_token(self._h, out.data_ptr(), self._stream()), "b200_engine_last_token")
+        return out
+
+    def decode(self, n_steps: int) -> torch.Tensor:
+        """n greedy steps on the device, each consuming the previous step's token → int64 [n] device tensor."""
+        out = torch.empty(n_steps, dtype=torch.int64, device=self.device)
+        check(lib().b200_engine_decode(self._h, n_steps, out.data_ptr(), self._stream()), "b200_engine_decode")
+        return out
+
+    # ------------------------------------------------------------------------------------------ generateSync
+    def generate_sync(self, prompt_ids: List[int] | torch.Tensor, max_new_tokens: int,
+                      pinned_in: Optional[torch.Tensor] = None, pinned_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """GPTEngine::generateSync for one sequence with HOST buffers: reset cache, H2D copy of the prompt ids,
+        prefill, (max_new_tokens - 1) decode steps, ONE D2H copy of the generated ids (like the reference, no
+        per-step host synchronisation).  Returns a CPU int64 tensor [max_new_tokens]."""
+        if max_new_tokens < 1:
+            raise B200Error("generate_sync: max_new_tokens must be >= 1")
+        prompt = torch.as_tensor(prompt_ids, dtype=torch.int64).view(1, -1)
+        if prompt.numel() == 0:
+            raise B200Error("generate_sync: empty prompt")
+        if pinned_in is None:
+            pinned_in = torch.empty(prompt.shape, dtype=torch.int64).pin_memory()
+        pinned_in.view(-1)[: prompt.numel()].copy_(prompt.view(-1))
+        ids_dev = pinned_in.view(-1)[: prompt.numel()].to(self.device, non_blocking=True).view(1, -1)
+        self.reset_cache()
+        first = self.gen_next_token(ids_dev)
+        rest = self.decode(max_new_tokens - 1)
+        toks = torch.cat([first.view(-1), rest])
+        if pinned_out is None:
+            pinned_out = torch.empty(max_new_tokens, dtype=torch.int64).pin_memory()
+        pinned_out[:max_new_tokens].copy_(toks, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return pinned_out[:max_new_tokens].clone()
