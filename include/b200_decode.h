@@ -123,14 +123,17 @@ int b200_gemv_fused_bf16(void* y, const void* x, const void* W, int64_t n, int64
 /* Decode attention of one layer for one new token (B = 1, Sq = 1), one launch:
  *   q|k|v = qkv  →  [q_norm/k_norm per head]  →  RoPE(q), RoPE(k) at position *pos  →  K/V row *pos written in place
  *   into kcache/vcache [max_ctx, Hkv, hd]  →  split-KV softmax(q kᵀ/√hd) v over rows 0…*pos  →  out [Hq*hd].
+ * The context is cut into splits of 256 (hd 64) / 128 (hd 128) keys, one CTA per (KV head, split).
+ * *pos must have been written before the kernel that produced `qkv` was launched (the kernel reads it, and the cached
+ * rows below it, ahead of its programmatic-dependency wait).
  * pos == NULL: plain attention over `fixed_len` cached rows, nothing appended, no rotation (rope_table may be NULL).
  * workspace: b200_attn_decode_workspace_bytes() bytes, ZERO-INITIALISED once by the caller (tickets self-reset).
  * [ref: src/layer/Attention.h:71-112,156-163; src/engine/CacheManager.h:24-42; TFA/mma/kernel.cuh:18-203] */
-int64_t b200_attn_decode_workspace_bytes(int64_t Hq, int64_t Hkv, int64_t hd, int64_t nsplit);
+int64_t b200_attn_decode_workspace_bytes(int64_t Hq, int64_t Hkv, int64_t hd, int64_t max_ctx);
 int b200_attn_decode_bf16(void* out, const void* qkv, const void* q_norm_or_null, const void* k_norm_or_null,
                           float eps, const float* rope_table, const int32_t* pos_or_null, int64_t fixed_len,
                           void* kcache, void* vcache, int64_t Hq, int64_t Hkv, int64_t hd, int64_t max_ctx,
-                          int64_t nsplit, void* workspace, void* stream);
+                          void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Boundary A — the whole per-token forward behind GPTModel::forward / GPTEngine::genNextToken.

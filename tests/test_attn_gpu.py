@@ -40,10 +40,10 @@ def test_attention_tinyfa_shapes(built_lib, B, Sq, Skv, Hq, Hkv, hd, causal):
     assert_close_bf16(got, want, 4, "attention vs oracle tile walk", atol=4e-3)
 
 
-@pytest.mark.parametrize("Hq,Hkv,hd,L,nsplit", [(14, 2, 64, 144, 8), (24, 8, 128, 240, 8), (16, 8, 128, 31, 4),
-                                                 (32, 8, 128, 129, 16), (4, 4, 64, 1, 8), (8, 1, 64, 500, 32),
-                                                 (6, 2, 128, 17, 1)])
-def test_attn_decode_plain(built_lib, Hq, Hkv, hd, L, nsplit):
+@pytest.mark.parametrize("Hq,Hkv,hd,L", [(14, 2, 64, 144), (24, 8, 128, 240), (16, 8, 128, 31), (32, 8, 128, 129),
+                                          (4, 4, 64, 1), (8, 1, 64, 500), (6, 2, 128, 17), (14, 2, 64, 257),
+                                          (16, 8, 128, 512), (14, 2, 64, 256)])
+def test_attn_decode_plain(built_lib, Hq, Hkv, hd, L):
     """pos == NULL mode: attention of one query row over `L` cached rows (no rotation, nothing appended)."""
     max_ctx = 512
     q = urand_bf16(1, 1, Hq, hd, seed=1)
@@ -52,8 +52,7 @@ def test_attn_decode_plain(built_lib, Hq, Hkv, hd, L, nsplit):
     vc = torch.zeros_like(kc)
     kc[:L], vc[:L] = k[0], v[0]
     qkv = torch.cat([q.view(-1), torch.zeros(2 * Hkv * hd, dtype=torch.bfloat16)])
-    got = ops.attn_decode(qkv.to(DEV), kc.to(DEV), vc.to(DEV), q_heads=Hq, kv_heads=Hkv, head_dim=hd, fixed_len=L,
-                          nsplit=nsplit).float().cpu().view(1, 1, Hq, hd)
+    got = ops.attn_decode(qkv.to(DEV), kc.to(DEV), vc.to(DEV), q_heads=Hq, kv_heads=Hkv, head_dim=hd, fixed_len=L).float().cpu().view(1, 1, Hq, hd)
     want = orc.flash_attention(q, k, v, False)
     assert_close_bf16(got, want, 4, "split-KV decode attention", atol=4e-3)
     naive = orc.naive_attention(q, k, v, False)
@@ -65,7 +64,7 @@ def test_attn_decode_plain(built_lib, Hq, Hkv, hd, L, nsplit):
 def test_attn_decode_fused_append(built_lib, Hq, Hkv, hd, qk_norm):
     """The engine's launch: raw qkv → [norm] → RoPE → append at *pos → attention, for several consecutive positions.
     K/V rows written to the cache must be bit-identical to the oracle's rope(k) / v (same table, ≤ 1 ulp FMA)."""
-    max_ctx, steps, start = 256, 5, 37
+    max_ctx, steps, start = 384, 5, 254  # crosses the 256-key (hd 64) / 128-key (hd 128) split boundaries
     table = orc.rope_table(hd, max_ctx, 1e6)
     g = torch.Generator().manual_seed(7)
     kc = torch.zeros(max_ctx, Hkv, hd, dtype=torch.bfloat16)
@@ -83,7 +82,7 @@ def test_attn_decode_fused_append(built_lib, Hq, Hkv, hd, qk_norm):
         pos.fill_(p)
         got = ops.attn_decode(qkv.to(DEV), kc_d, vc_d, q_heads=Hq, kv_heads=Hkv, head_dim=hd, pos=pos,
                               rope_table=table.to(DEV), q_norm=None if qn is None else qn.to(DEV),
-                              k_norm=None if kn is None else kn.to(DEV), eps=1e-6, nsplit=8).float().cpu()
+                              k_norm=None if kn is None else kn.to(DEV), eps=1e-6).float().cpu()
         q = qkv[: Hq * hd].view(1, 1, Hq, hd)
         k = qkv[Hq * hd: (Hq + Hkv) * hd].view(1, 1, Hkv, hd)
         v = qkv[(Hq + Hkv) * hd:].view(1, 1, Hkv, hd)

@@ -52,7 +52,7 @@ PROTOTYPES = {
     "b200_argmax_bf16": (I32, [P, P, I64, I64, P, P]),
     "b200_gemv_fused_bf16": (I32, [P, P, P, I64, I64, I32, P, F, P, P, I32, P]),
     "b200_attn_decode_workspace_bytes": (I64, [I64, I64, I64, I64]),
-    "b200_attn_decode_bf16": (I32, [P, P, P, P, F, P, P, I64, P, P, I64, I64, I64, I64, I64, P, P]),
+    "b200_attn_decode_bf16": (I32, [P, P, P, P, F, P, P, I64, P, P, I64, I64, I64, I64, P, P]),
     "b200_engine_create": (I32, [C.POINTER(ModelDesc), C.POINTER(WeightTable), C.POINTER(P)]),
     "b200_engine_destroy": (None, [P]),
     "b200_engine_reset": (I32, [P, P]),

@@ -68,19 +68,18 @@ int b200_gemv_fused_bf16(void* y, const void* x, const void* W, int64_t n, int64
   return gemv_launch(plan, (cudaStream_t)stream, false);
 }
 
-int64_t b200_attn_decode_workspace_bytes(int64_t Hq, int64_t Hkv, int64_t hd, int64_t nsplit) {
-  if (Hkv <= 0 || Hq % Hkv != 0) return -1;
-  return b200::attn_decode_ws_floats((int)Hq, (int)Hkv, (int)hd, (int)nsplit) * 4 + ((Hkv * 4 + 15) / 16) * 16;
+int64_t b200_attn_decode_workspace_bytes(int64_t Hq, int64_t Hkv, int64_t hd, int64_t max_ctx) {
+  if (Hkv <= 0 || Hq % Hkv != 0 || (hd != 64 && hd != 128) || max_ctx < 1) return -1;
+  const int nsplit = b200::attn_decode_nsplit((int)hd, (int)max_ctx);
+  return b200::attn_decode_ws_floats((int)Hq, (int)Hkv, (int)hd, nsplit) * 4 + ((Hkv * 4 + 15) / 16) * 16;
 }
 
 int b200_attn_decode_bf16(void* out, const void* qkv, const void* q_norm, const void* k_norm, float eps,
                           const float* rope_table, const int32_t* pos, int64_t fixed_len, void* kcache, void* vcache,
-                          int64_t Hq, int64_t Hkv, int64_t hd, int64_t max_ctx, int64_t nsplit, void* workspace,
-                          void* stream) {
+                          int64_t Hq, int64_t Hkv, int64_t hd, int64_t max_ctx, void* workspace, void* stream) {
   using namespace b200;
   B200_CHECK_ARG(out && qkv && kcache && vcache && workspace, "attn_decode: null pointer");
   B200_CHECK_ARG(pos != nullptr || (fixed_len >= 1 && fixed_len <= max_ctx), "attn_decode: fixed_len out of range");
-  B200_CHECK_ARG(nsplit >= 1 && nsplit <= 64, "attn_decode: nsplit out of range");
   int rc = b200_device_check();
   if (rc != B200_OK) return rc;
   if ((rc = attn_setup_attributes()) != B200_OK) return rc;
@@ -99,9 +98,8 @@ int b200_attn_decode_bf16(void* out, const void* qkv, const void* q_norm, const 
   a.ws = (float*)((uint8_t*)workspace + ((Hkv * 4 + 15) / 16) * 16);
   a.Hq = (int)Hq;
   a.Hkv = (int)Hkv;
-  a.nsplit = (int)nsplit;
+  a.nsplit = attn_decode_nsplit((int)hd, (int)max_ctx);
   a.max_ctx = (int)max_ctx;
-  a.min_chunk = 16;
   return launch_attn_decode(a, (int)hd, (cudaStream_t)stream, false);
 }
 

@@ -37,46 +37,86 @@ struct InvSqrtHd<128> {
   static constexpr float value = 0.08838834764831845f;
 };
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// keys per split: fixed by the shared-memory staging buffers (K and V of one split = 64 KB for both head dims)
+template <int HD>
+struct SplitKeys {
+  static constexpr int value = (HD == 64) ? 256 : 128;
+};
+
 template <int HD, int G>
 __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnDecodeParams p) {
   constexpr int LPK = HD / 8;           // lanes per key row (16-byte pieces)
   constexpr int KPW = 32 / LPK;         // keys per warp per iteration
   constexpr int NSLOT = kAttnThreads / LPK;
   constexpr int EPL = HD / 32;          // elements per lane when a warp owns one head vector
+  constexpr int CHUNK = SplitKeys<HD>::value;
   constexpr float kScale = InvSqrtHd<HD>::value * kLog2e;
 
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  float* q_s = reinterpret_cast<float*>(smem_raw);                        // [G][HD]
+  __nv_bfloat16* kbuf = reinterpret_cast<__nv_bfloat16*>(smem_raw);      // [CHUNK][HD]
+  __nv_bfloat16* vbuf = kbuf + CHUNK * HD;                                // [CHUNK][HD]
+  float* q_s = reinterpret_cast<float*>(vbuf + CHUNK * HD);               // [G][HD]
   float* pv_red = q_s + G * HD;                                           // [8][G][HD]
-  float* ml = pv_red + kAttnWarps * G * HD;                               // [G][2]
-  __nv_bfloat16* knew_s = reinterpret_cast<__nv_bfloat16*>(ml + 2 * G);   // [HD]
-  __nv_bfloat16* vnew_s = knew_s + HD;                                    // [HD]
-  float* sc = reinterpret_cast<float*>(vnew_s + HD);                      // [G][chunk_cap]
+  float* sc = pv_red + kAttnWarps * G * HD;                               // [G][CHUNK]
+  float* ml = sc + G * CHUNK;                                             // [G][2]
   __shared__ bool is_last;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int kvh = blockIdx.y, split = blockIdx.x;
 
   pdl_trigger();
-  pdl_wait();
-
+  // *p.pos was written by the PREVIOUS token's last kernel (or by reset/seek), i.e. before this graph launch began, so
+  // it may be read ahead of griddepcontrol.wait — and with it every cached K/V row below pos.
   const bool append = (p.pos != nullptr);
   const int pos = append ? *p.pos : p.fixed_len - 1;
   const int L = pos + 1;
-  int chunk = (L + p.nsplit - 1) / p.nsplit;
-  chunk = max(chunk, p.min_chunk);
-  const int nact = (L + chunk - 1) / chunk;
-  if (split >= nact) return;
-  const int start = split * chunk;
-  const int end = min(L, start + chunk);
-  const int chunk_cap = max((p.max_ctx + p.nsplit - 1) / p.nsplit, p.min_chunk);
+  const int nact = (L + CHUNK - 1) / CHUNK;
+  if (split >= nact) {
+    pdl_wait();
+    return;
+  }
+  const int start = split * CHUNK;
+  const int end = min(L, start + CHUNK);
+  const int nk = end - start;
+  const int n_old = append ? min(end, pos) - start : nk;  // rows already in the cache
+
+  // ---- stage the cached K/V rows of this split in shared memory (cp.async), overlapping the producer kernel
+  {
+    const int pieces = n_old * LPK;
+    for (int i = tid; i < pieces; i += kAttnThreads) {
+      const int r = i / LPK, c = i % LPK;
+      const size_t g = ((size_t)(start + r) * p.Hkv + kvh) * HD + c * 8;
+      cp_async16(kbuf + r * HD + c * 8, p.kcache + g);
+      cp_async16(vbuf + r * HD + c * 8, p.vcache + g);
+    }
+    cp_async_commit();
+  }
+  // RoPE row of this position (constant table)
+  float rc[EPL / 2], rs[EPL / 2];
+  if (p.rope != nullptr) {
+    const float* row = p.rope + (size_t)pos * HD * 2;
+#pragma unroll
+    for (int j = 0; j < EPL / 2; ++j) {
+      rc[j] = row[(lane + 32 * j) * 2];
+      rs[j] = row[(lane + 32 * j) * 2 + 1];
+    }
+  }
+
+  pdl_wait();  // qkv of this token is complete and visible from here on
 
   const int qdim = p.Hq * HD, kvdim = p.Hkv * HD;
+  const bool owns_new = append && (pos >= start) && (pos < end);
 
-  // ---- q heads (and the new k/v) : optional per-head RMSNorm, then RoPE, with the reference's roundings
+  // ---- q heads (and the new k/v): optional per-head RMSNorm, then RoPE, with the reference's roundings
   for (int h = warp; h < G + 1; h += kAttnWarps) {
     const bool is_k = (h == G);
-    if (is_k && !append) break;
+    if (is_k && !owns_new) break;
     const __nv_bfloat16* src = is_k ? p.qkv + qdim + kvh * HD : p.qkv + (kvh * G + h) * HD;
     const __nv_bfloat16* nw = is_k ? p.k_norm : p.q_norm;
     float x[EPL];
@@ -92,36 +132,35 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnDec
       for (int j = 0; j < EPL; ++j) x[j] = round_bf16(x[j] * inv * bf16_to_f(nw[lane + 32 * j]));
     }
     if (p.rope != nullptr) {
-      const float* row = p.rope + (size_t)pos * HD * 2;
 #pragma unroll
       for (int j = 0; j < EPL / 2; ++j) {
-        const int i = lane + 32 * j;  // index inside the first half
-        const float c = row[i * 2], s = row[i * 2 + 1];
         const float x1 = x[j], x2 = x[j + EPL / 2];
-        x[j] = round_bf16(x1 * c - x2 * s);
-        x[j + EPL / 2] = round_bf16(x2 * c + x1 * s);
+        x[j] = round_bf16(x1 * rc[j] - x2 * rs[j]);
+        x[j + EPL / 2] = round_bf16(x2 * rc[j] + x1 * rs[j]);
       }
     }
     if (is_k) {
+      // the new row goes to its slot of the staged split and, in place, to the cache in HBM
+      __nv_bfloat16* krow = kbuf + (pos - start) * HD;
+      __nv_bfloat16* vrow = vbuf + (pos - start) * HD;
+      __nv_bfloat16* kg = p.kcache + ((size_t)pos * p.Hkv + kvh) * HD;
+      __nv_bfloat16* vg = p.vcache + ((size_t)pos * p.Hkv + kvh) * HD;
 #pragma unroll
       for (int j = 0; j < EPL; ++j) {
-        knew_s[lane + 32 * j] = f_to_bf16(x[j]);
-        vnew_s[lane + 32 * j] = p.qkv[qdim + kvdim + kvh * HD + lane + 32 * j];
+        const __nv_bfloat16 kk = f_to_bf16(x[j]);
+        const __nv_bfloat16 vv = p.qkv[qdim + kvdim + kvh * HD + lane + 32 * j];
+        krow[lane + 32 * j] = kk;
+        vrow[lane + 32 * j] = vv;
+        kg[lane + 32 * j] = kk;
+        vg[lane + 32 * j] = vv;
       }
     } else {
 #pragma unroll
       for (int j = 0; j < EPL; ++j) q_s[h * HD + lane + 32 * j] = x[j];
     }
   }
+  cp_async_wait_all();
   __syncthreads();
-
-  // the split that holds position `pos` appends the new K/V row to the cache
-  if (append && split == nact - 1 && tid < 2 * (HD / 8)) {
-    const int which = tid / (HD / 8), piece = tid % (HD / 8);
-    const uint4 v = reinterpret_cast<const uint4*>(which ? vnew_s : knew_s)[piece];
-    __nv_bfloat16* dst = (which ? p.vcache : p.kcache) + ((size_t)pos * p.Hkv + kvh) * HD;
-    reinterpret_cast<uint4*>(dst)[piece] = v;
-  }
 
   // ---- scores: LPK lanes cooperate on one key row, all G query heads at once
   {
@@ -131,31 +170,25 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnDec
     for (int g = 0; g < G; ++g)
 #pragma unroll
       for (int e = 0; e < 8; ++e) qf[g][e] = q_s[g * HD + part * 8 + e];
-    for (int j0 = start + warp * KPW; j0 < end; j0 += kAttnWarps * KPW) {
+    for (int j0 = warp * KPW; j0 < nk; j0 += kAttnWarps * KPW) {
       const int j = j0 + sub;
-      const bool valid = j < end;
+      const bool valid = j < nk;
       uint4 kv = make_uint4(0, 0, 0, 0);
-      if (valid) {
-        if (append && j == pos)
-          kv = reinterpret_cast<const uint4*>(knew_s)[part];
-        else
-          kv = reinterpret_cast<const uint4*>(p.kcache + ((size_t)j * p.Hkv + kvh) * HD)[part];
-      }
+      if (valid) kv = *reinterpret_cast<const uint4*>(kbuf + j * HD + part * 8);
 #pragma unroll
       for (int g = 0; g < G; ++g) {
         float d = dot8(kv, qf[g], 0.f);
 #pragma unroll
         for (int o = LPK / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-        if (valid && part == 0) sc[g * chunk_cap + (j - start)] = d;
+        if (valid && part == 0) sc[g * CHUNK + j] = d;
       }
     }
   }
   __syncthreads();
 
   // ---- softmax inside the split (base-2 exponent like the reference): warp g owns head g
-  const int nk = end - start;
   for (int g = warp; g < G; g += kAttnWarps) {
-    float* s = sc + g * chunk_cap;
+    float* s = sc + g * CHUNK;
     float m = -INFINITY;
     for (int j = lane; j < nk; j += 32) m = fmaxf(m, s[j]);
     m = warp_max(m);
@@ -182,17 +215,13 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnDec
     for (int g = 0; g < G; ++g)
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[g][e] = 0.f;
-    for (int j = start + slot; j < end; j += NSLOT) {
-      uint4 vv;
-      if (append && j == pos)
-        vv = reinterpret_cast<const uint4*>(vnew_s)[part];
-      else
-        vv = reinterpret_cast<const uint4*>(p.vcache + ((size_t)j * p.Hkv + kvh) * HD)[part];
+    for (int j = slot; j < nk; j += NSLOT) {
+      const uint4 vv = *reinterpret_cast<const uint4*>(vbuf + j * HD + part * 8);
       float vf[8];
       unpack8(vv, vf);
 #pragma unroll
       for (int g = 0; g < G; ++g) {
-        const float pj = sc[g * chunk_cap + (j - start)];
+        const float pj = sc[g * CHUNK + j];
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[g][e] = fmaf(pj, vf[e], acc[g][e]);
       }
@@ -259,11 +288,6 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnDec
     p.out[(kvh * G + g) * HD + d] = f_to_bf16(num * (den > 0.f ? 1.f / den : 0.f));
   }
   if (tid == 0) p.tickets[kvh] = 0;
-}
-
-template <int HD, int G>
-size_t attn_decode_smem(int chunk_cap) {
-  return (size_t)(G * HD + kAttnWarps * G * HD + 2 * G) * 4 + 2 * HD * 2 + (size_t)G * chunk_cap * 4;
 }
 
 using AttnFn = void (*)(const AttnDecodeParams);
@@ -357,7 +381,9 @@ int attn_setup_attributes() {
     for (int g : gs) {
       AttnFn fns[2] = {pick_attn<64>(g), pick_attn<128>(g)};
       for (AttnFn f : fns) {
-        cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+        if (e == cudaSuccess)
+          e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) {
           set_error("cudaFuncSetAttribute(attn smem) failed: %s", cudaGetErrorString(e));
           rc = B200_ERR_CUDA;
@@ -370,6 +396,11 @@ int attn_setup_attributes() {
   return rc;
 }
 
+int attn_decode_nsplit(int hd, int max_ctx) {
+  const int chunk = (hd == 64) ? SplitKeys<64>::value : SplitKeys<128>::value;
+  return std::max(1, (max_ctx + chunk - 1) / chunk);
+}
+
 int launch_attn_decode(const AttnDecodeParams& p, int hd, cudaStream_t st, bool pdl) {
   B200_CHECK_ARG(hd == 64 || hd == 128, "attention: head_dim %d not built (64 and 128 are, like the reference)", hd);
   B200_CHECK_ARG(p.Hkv > 0 && p.Hq % p.Hkv == 0, "attention: Hq=%d must be a multiple of Hkv=%d", p.Hq, p.Hkv);
@@ -379,11 +410,12 @@ int launch_attn_decode(const AttnDecodeParams& p, int hd, cudaStream_t st, bool 
     set_error("attention: group size Hq/Hkv=%d not built (1,2,3,4,7,8 are)", G);
     return B200_ERR_UNSUPPORTED;
   }
-  B200_CHECK_ARG(p.nsplit >= 1 && p.min_chunk >= 1 && p.max_ctx >= 1, "attention: bad split configuration");
-  const int chunk_cap = std::max((p.max_ctx + p.nsplit - 1) / p.nsplit, p.min_chunk);
-  size_t smem = (size_t)(G * hd + kAttnWarps * G * hd + 2 * G) * 4 + 2 * hd * 2 + (size_t)G * chunk_cap * 4;
-  B200_CHECK_ARG(smem <= 160 * 1024, "attention: context %d with %d splits needs %zu bytes of shared memory", p.max_ctx,
-                 p.nsplit, smem);
+  const int chunk = (hd == 64) ? SplitKeys<64>::value : SplitKeys<128>::value;
+  B200_CHECK_ARG(p.max_ctx >= 1 && p.nsplit == attn_decode_nsplit(hd, p.max_ctx),
+                 "attention: nsplit %d does not match max_ctx %d (need %d)", p.nsplit, p.max_ctx,
+                 attn_decode_nsplit(hd, p.max_ctx));
+  B200_CHECK_ARG(p.nsplit <= 65535, "attention: context too long");
+  const size_t smem = (size_t)2 * chunk * hd * 2 + (size_t)(G * hd + kAttnWarps * G * hd + G * chunk + 2 * G) * 4;
   B200_CUDA(launch_pdl(f, dim3(p.nsplit, p.Hkv), dim3(kAttnThreads), smem, st, pdl, p));
   return B200_OK;
 }

@@ -40,8 +40,8 @@ struct b200_engine {
   void* argmax_ws = nullptr;
   int64_t* cur_tok = nullptr;   // token the next step consumes
   int64_t* gen_log = nullptr;   // ring of generated tokens
-  int* pos_next = nullptr;      // position the next token will occupy
-  int* pos_cur = nullptr;       // position of the token in flight (read by attention)
+  int* pos = nullptr;           // position of the token in flight; advanced by the LAST kernel of each token, so it
+                                // is stable (and readable ahead of griddepcontrol.wait) for the whole next token
   unsigned long long* gen_count = nullptr;
   int gen_cap = 0;
   int nsplit = 1;
@@ -63,11 +63,10 @@ namespace b200 {
 
 namespace {
 
-// embed: x = E[cur_tok]; pos_cur = pos_next++   (first kernel of every token)
+// embed: x = E[cur_tok]   (first kernel of every token)
 __global__ void __launch_bounds__(128) embed_step_kernel(__nv_bfloat16* __restrict__ x,
                                                          const __nv_bfloat16* __restrict__ table,
-                                                         const int64_t* __restrict__ tok, int64_t V, int H,
-                                                         int* pos_next, int* pos_cur) {
+                                                         const int64_t* __restrict__ tok, int64_t V, int H) {
   pdl_trigger();
   pdl_wait();
   int64_t id = *tok;
@@ -75,23 +74,6 @@ __global__ void __launch_bounds__(128) embed_step_kernel(__nv_bfloat16* __restri
   const uint4* s4 = reinterpret_cast<const uint4*>(table + id * H);
   uint4* d4 = reinterpret_cast<uint4*>(x);
   for (int i = threadIdx.x; i < (H >> 3); i += blockDim.x) d4[i] = s4[i];
-  if (threadIdx.x == 0) {
-    const int p = *pos_next;
-    *pos_cur = p;
-    *pos_next = p + 1;
-  }
-}
-
-// after argmax: publish the greedy token as the next input and log it
-__global__ void publish_token_kernel(const int64_t* __restrict__ argmax_out, int64_t* cur_tok, int64_t* gen_log,
-                                     unsigned long long* gen_count, int gen_cap) {
-  pdl_trigger();
-  pdl_wait();
-  const int64_t t = *argmax_out;
-  *cur_tok = t;
-  const unsigned long long c = *gen_count;
-  gen_log[c % (unsigned long long)gen_cap] = t;
-  *gen_count = c + 1;
 }
 
 }  // namespace
@@ -100,8 +82,11 @@ static int engine_launch_token(b200_engine* e, cudaStream_t st, bool with_head) 
   const b200_model_desc& d = e->d;
   const bool pdl = e->use_pdl;
   int rc;
-  B200_CUDA(launch_pdl(embed_step_kernel, dim3(1), dim3(128), 0, st, pdl, e->x, e->embed, (const int64_t*)e->cur_tok,
-                       (int64_t)d.vocab, (int)d.hidden, e->pos_next, e->pos_cur));
+  // NOTE (measured on B200, CUDA 12.9 / driver 580): when the LAST kernel node of a captured graph has a programmatic
+  // (PDL) incoming edge, work enqueued after the graph launch can start before that node has finished.  The last
+  // launch of each graph therefore uses a normal full dependency, and so does the first (it has no upstream).
+  B200_CUDA(launch_pdl(embed_step_kernel, dim3(1), dim3(128), 0, st, false, e->x, e->embed, (const int64_t*)e->cur_tok,
+                       (int64_t)d.vocab, (int)d.hidden));
   const size_t kv_layer = (size_t)d.max_ctx * e->Hkv_l * d.head_dim;
   for (int l = 0; l < d.layers; ++l) {
     if ((rc = gemv_launch(e->p_qkv[l], st, pdl)) != B200_OK) return rc;
@@ -111,7 +96,7 @@ static int engine_launch_token(b200_engine* e, cudaStream_t st, bool with_head) 
     a.k_norm = (const __nv_bfloat16*)e->lw[l].k_norm;
     a.eps = d.rms_eps;
     a.rope = e->rope;
-    a.pos = e->pos_cur;
+    a.pos = e->pos;
     a.fixed_len = 0;
     a.kcache = e->kcache + (size_t)l * kv_layer;
     a.vcache = e->vcache + (size_t)l * kv_layer;
@@ -122,18 +107,24 @@ static int engine_launch_token(b200_engine* e, cudaStream_t st, bool with_head) 
     a.Hkv = e->Hkv_l;
     a.nsplit = e->nsplit;
     a.max_ctx = d.max_ctx;
-    a.min_chunk = 16;
     if ((rc = launch_attn_decode(a, d.head_dim, st, pdl)) != B200_OK) return rc;
     if ((rc = gemv_launch(e->p_o[l], st, pdl)) != B200_OK) return rc;
     if ((rc = gemv_launch(e->p_gu[l], st, pdl)) != B200_OK) return rc;
-    if ((rc = gemv_launch(e->p_down[l], st, pdl)) != B200_OK) return rc;
+    const bool last_node = !with_head && l == d.layers - 1;
+    GemvPlan dn = e->p_down[l];
+    dn.p.pos_inc = last_node ? e->pos : nullptr;  // the LAST kernel of a token advances the position
+    if ((rc = gemv_launch(dn, st, pdl && !last_node)) != B200_OK) return rc;
   }
   if (with_head) {
     if ((rc = gemv_launch(e->p_head, st, pdl)) != B200_OK) return rc;
     int64_t* amax = reinterpret_cast<int64_t*>((uint8_t*)e->argmax_ws + argmax_workspace_bytes(1, e->V_l));
-    if ((rc = launch_argmax(amax, e->logits, 1, e->V_l, e->argmax_ws, st, pdl)) != B200_OK) return rc;
-    B200_CUDA(launch_pdl(publish_token_kernel, dim3(1), dim3(1), 0, st, pdl, (const int64_t*)amax, e->cur_tok,
-                         e->gen_log, e->gen_count, e->gen_cap));
+    ArgmaxPublish pub;
+    pub.pos = e->pos;
+    pub.cur_tok = e->cur_tok;
+    pub.gen_log = e->gen_log;
+    pub.gen_count = e->gen_count;
+    pub.gen_cap = e->gen_cap;
+    if ((rc = launch_argmax(amax, e->logits, 1, e->V_l, e->argmax_ws, st, false, &pub)) != B200_OK) return rc;
   }
   return B200_OK;
 }
@@ -177,7 +168,7 @@ static int engine_run_token(b200_engine* e, cudaStream_t st, bool with_head) {
   if (e->use_graph) {
     cudaGraphExec_t g = with_head ? e->g_step : e->g_body;
     B200_CUDA(cudaGraphLaunch(g, st));
-    g_launches.fetch_add(with_head ? e->launches_per_token : e->launches_per_token - 3);
+    g_launches.fetch_add(with_head ? e->launches_per_token : e->launches_per_token - 2);
     return B200_OK;
   }
   return engine_launch_token(e, st, with_head);
@@ -244,10 +235,7 @@ static int engine_build(const b200_model_desc* desc, const b200_weight_table* w,
   if ((rc = gemv_setup_attributes()) != B200_OK) return rc;
   if ((rc = attn_setup_attributes()) != B200_OK) return rc;
 
-  // split-KV: enough CTAs to cover the GPU, at least 16 keys per split
-  e->nsplit = std::max(1, std::min(32, (e->num_sms + e->Hkv_l - 1) / e->Hkv_l));
-  env = std::getenv("B200_ATTN_NSPLIT");
-  if (env) e->nsplit = std::max(1, std::min(64, std::atoi(env)));
+  e->nsplit = attn_decode_nsplit(d.head_dim, d.max_ctx);
   e->gen_cap = 1 << 16;
 
   // ---- one arena for everything the engine owns
@@ -287,8 +275,7 @@ static int engine_build(const b200_model_desc* desc, const b200_weight_table* w,
   e->argmax_ws = (void*)(e->arena + o_amax);
   e->cur_tok = (int64_t*)(e->arena + o_tok);
   e->gen_log = (int64_t*)(e->arena + o_log);
-  e->pos_next = (int*)(e->arena + o_pos);
-  e->pos_cur = e->pos_next + 1;
+  e->pos = (int*)(e->arena + o_pos);
   e->gen_count = (unsigned long long*)(e->arena + o_cnt);
 
   // ---- GEMV plans (TMA descriptors are encoded once, here)
@@ -341,7 +328,7 @@ static int engine_build(const b200_model_desc* desc, const b200_weight_table* w,
   e->p_head.p.eps = d.rms_eps;
   e->p_head.p.y = e->logits;
 
-  e->launches_per_token = 1 + 5 * d.layers + 3;
+  e->launches_per_token = 1 + 5 * d.layers + 2;
   if (e->use_graph) {
     if ((rc = engine_capture(e, true, &e->g_step)) != B200_OK) return rc;
     if ((rc = engine_capture(e, false, &e->g_body)) != B200_OK) return rc;
@@ -371,7 +358,7 @@ void b200_engine_destroy(b200_engine* e) {
 int b200_engine_reset(b200_engine* e, void* stream) {
   using namespace b200;
   B200_CHECK_ARG(e, "engine_reset: null engine");
-  B200_CUDA(cudaMemsetAsync(e->pos_next, 0, 16, (cudaStream_t)stream));
+  B200_CUDA(cudaMemsetAsync(e->pos, 0, 16, (cudaStream_t)stream));
   e->h_pos = 0;
   return B200_OK;
 }
@@ -386,7 +373,7 @@ int b200_engine_seek(b200_engine* e, int64_t position, void* stream) {
   }
   const int v[2] = {(int)position, (int)position};
   // small enough to travel in the command stream; stream-ordered with the graphs that read it
-  B200_CUDA(cudaMemcpyAsync(e->pos_next, v, 8, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  B200_CUDA(cudaMemcpyAsync(e->pos, v, 8, cudaMemcpyHostToDevice, (cudaStream_t)stream));
   e->h_pos = position;
   return B200_OK;
 }

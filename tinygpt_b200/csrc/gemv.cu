@@ -232,6 +232,8 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
     }
   }
 
+  if (p.pos_inc != nullptr && blockIdx.x == 0 && ctid == 0) *p.pos_inc += 1;
+
   if constexpr (EPI == EPI_TP_PUSH) {
     __threadfence_system();
     named_bar_sync(1, kConsumers);
@@ -287,6 +289,11 @@ int gemv_setup_attributes() {
             KernelFn f = pick(rpw, nseg, pro, epi);
             if (!f) continue;
             cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 4096);
+            // one carveout for every kernel of the token: a change of carveout between launches drains the SM and
+            // would serialise the PDL overlap
+            if (e == cudaSuccess)
+              e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       cudaSharedmemCarveoutMaxShared);
             if (e != cudaSuccess) {
               set_error("cudaFuncSetAttribute(gemv smem) failed: %s", cudaGetErrorString(e));
               rc = B200_ERR_CUDA;

@@ -31,6 +31,7 @@ struct GemvParams {
   int seg_rows;                   // row offset of segment 1 inside W (NSEG == 2: gate rows | up rows)
   int rowblocks;                  // ceil(n / (8 * RPW))
   int stages;                     // depth of the shared-memory ring
+  int* pos_inc;                   // engine: when set, CTA 0 advances the token position after its last row block
   // ---- tensor-parallel exchange (peer-mapped windows over NVLink), see tp.cuh
   float* tp_push[kMaxTpWorld];            // EPI_TP_PUSH: slot for MY partial inside rank r's window ([n] floats)
   unsigned long long* tp_flag[kMaxTpWorld];  // EPI_TP_PUSH: rank r's arrival counter for this exchange point

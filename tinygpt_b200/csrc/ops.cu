@@ -153,7 +153,7 @@ __device__ __forceinline__ void argmax_merge(float& v, int64_t& i, float ov, int
 
 __global__ void __launch_bounds__(256) argmax_kernel(int64_t* __restrict__ out, const __nv_bfloat16* __restrict__ logits,
                                                      int64_t V, float* __restrict__ ws_val, int64_t* __restrict__ ws_idx,
-                                                     unsigned int* __restrict__ ticket) {
+                                                     unsigned int* __restrict__ ticket, const ArgmaxPublish pub) {
   __shared__ float sv[8];
   __shared__ int64_t si[8];
   __shared__ bool last;
@@ -209,6 +209,14 @@ __global__ void __launch_bounds__(256) argmax_kernel(int64_t* __restrict__ out, 
   if (threadIdx.x == 0) {
     out[row] = idx;
     ticket[row] = 0;  // self-reset for the next launch
+    if (pub.cur_tok != nullptr && row == 0) {
+      // engine: the greedy token becomes the next step's input and is appended to the on-device log
+      *pub.cur_tok = idx;
+      if (pub.pos != nullptr) *pub.pos += 1;
+      const unsigned long long c = *pub.gen_count;
+      pub.gen_log[c % (unsigned long long)pub.gen_cap] = idx;
+      *pub.gen_count = c + 1;
+    }
   }
 }
 
@@ -288,7 +296,7 @@ int64_t argmax_workspace_bytes(int64_t rows, int64_t V) {
 }
 
 int launch_argmax(int64_t* idx, const void* logits, int64_t rows, int64_t V, void* workspace, cudaStream_t st,
-                  bool pdl) {
+                  bool pdl, const ArgmaxPublish* pub) {
   B200_CHECK_ARG(idx && logits && workspace && rows > 0 && V > 0 && rows < 65536, "argmax: bad arguments");
   const int c = argmax_chunks(V);
   uint8_t* ws = (uint8_t*)workspace;
@@ -296,7 +304,7 @@ int launch_argmax(int64_t* idx, const void* logits, int64_t rows, int64_t V, voi
   int64_t* wi = (int64_t*)(ws + ((rows * c * 4 + 15) / 16) * 16);
   unsigned int* ticket = (unsigned int*)((uint8_t*)wi + rows * c * 8);
   B200_CUDA(launch_pdl(argmax_kernel, dim3(c, (unsigned)rows), dim3(256), 0, st, pdl, idx,
-                       (const __nv_bfloat16*)logits, V, wv, wi, ticket));
+                       (const __nv_bfloat16*)logits, V, wv, wi, ticket, pub ? *pub : ArgmaxPublish{}));
   return B200_OK;
 }
 
@@ -346,7 +354,7 @@ int b200_embedding_bf16(void* y, const void* table, const int64_t* ids, int64_t 
 int64_t b200_argmax_workspace_bytes(int64_t rows, int64_t V) { return b200::argmax_workspace_bytes(rows, V); }
 
 int b200_argmax_bf16(int64_t* idx, const void* logits, int64_t rows, int64_t V, void* workspace, void* stream) {
-  return b200::launch_argmax(idx, logits, rows, V, workspace, (cudaStream_t)stream, false);
+  return b200::launch_argmax(idx, logits, rows, V, workspace, (cudaStream_t)stream, false, nullptr);
 }
 
 }  // extern "C"

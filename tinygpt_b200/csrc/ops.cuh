@@ -14,8 +14,16 @@ int launch_embedding(void* y, const void* table, const int64_t* ids, int64_t n_i
                      cudaStream_t st, bool pdl);
 int argmax_chunks(int64_t V);
 int64_t argmax_workspace_bytes(int64_t rows, int64_t V);
+// Optional tail of the engine's argmax: the last CTA publishes the greedy token as the next step's input.
+struct ArgmaxPublish {
+  int* pos = nullptr;  // position counter advanced for the next token
+  int64_t* cur_tok = nullptr;
+  int64_t* gen_log = nullptr;
+  unsigned long long* gen_count = nullptr;
+  int gen_cap = 1;
+};
 int launch_argmax(int64_t* idx, const void* logits, int64_t rows, int64_t V, void* workspace, cudaStream_t st,
-                  bool pdl);
+                  bool pdl, const ArgmaxPublish* pub);
 
 // ---- attention (attn.cu)
 // Fused decode attention of one layer for one new token (B = 1, Sq = 1):
@@ -27,16 +35,17 @@ struct AttnDecodeParams {
   const __nv_bfloat16* k_norm;   // [hd] or null
   float eps;
   const float* rope;             // [max_ctx, hd, 2] fp32 table, or null (no rotation: stand-alone attention op)
-  const int* pos;                // device scalar: past length (index of the new token); null ⇒ fixed_len - 1
+  const int* pos;                // device scalar: past length (index of the new token), stable since BEFORE the
+                                 // producer kernel started (see engine.cu); null ⇒ fixed_len - 1
   int fixed_len;                 // used when pos == null: number of keys, nothing is appended
   __nv_bfloat16* kcache;         // [max_ctx, Hkv, hd]
   __nv_bfloat16* vcache;         // [max_ctx, Hkv, hd]
   __nv_bfloat16* out;            // [Hq*hd]
   float* ws;                     // split partials: [Hkv][nsplit][G][hd + 2] floats
   unsigned int* tickets;         // [Hkv], zero-initialised, self-resetting
-  int Hq, Hkv, nsplit, max_ctx;
-  int min_chunk;                 // keys per split at least this many
+  int Hq, Hkv, nsplit, max_ctx;  // nsplit = attn_decode_nsplit(hd, max_ctx): fixed 256 (hd 64) / 128 (hd 128) keys per split
 };
+int attn_decode_nsplit(int hd, int max_ctx);
 int launch_attn_decode(const AttnDecodeParams& p, int hd, cudaStream_t st, bool pdl);
 int64_t attn_decode_ws_floats(int Hq, int Hkv, int hd, int nsplit);
 int attn_setup_attributes();

@@ -159,15 +159,15 @@ def gemv_fused(x, weight, *, norm_weight=None, eps=0.0, bias=None, residual=None
 
 
 def attn_decode(qkv, kcache, vcache, *, q_heads, kv_heads, head_dim, pos=None, fixed_len=0, rope_table=None,
-                q_norm=None, k_norm=None, eps=0.0, nsplit=8) -> torch.Tensor:
+                q_norm=None, k_norm=None, eps=0.0) -> torch.Tensor:
     """Fused decode attention of one layer (see include/b200_decode.h b200_attn_decode_bf16)."""
     qkv, kcache, vcache = _chk(qkv, "attn_decode.qkv"), _chk(kcache, "attn_decode.kcache"), _chk(vcache, "attn_decode.vcache")
     max_ctx = kcache.shape[0]
-    ws = torch.zeros(lib().b200_attn_decode_workspace_bytes(q_heads, kv_heads, head_dim, nsplit), dtype=torch.uint8,
+    ws = torch.zeros(lib().b200_attn_decode_workspace_bytes(q_heads, kv_heads, head_dim, max_ctx), dtype=torch.uint8,
                      device=qkv.device)
     out = torch.empty(q_heads * head_dim, dtype=torch.bfloat16, device=qkv.device)
     check(lib().b200_attn_decode_bf16(out.data_ptr(), qkv.data_ptr(), _ptr(q_norm), _ptr(k_norm), float(eps),
                                       _ptr(rope_table), _ptr(pos), int(fixed_len), kcache.data_ptr(),
-                                      vcache.data_ptr(), q_heads, kv_heads, head_dim, max_ctx, nsplit, ws.data_ptr(),
+                                      vcache.data_ptr(), q_heads, kv_heads, head_dim, max_ctx, ws.data_ptr(),
                                       _stream()), "b200_attn_decode_bf16")
     return out
