@@ -101,19 +101,38 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
     return;
   }
 
-  // -------------------------------------------------------------------- consumers: wait for the producer kernel
-  pdl_wait();
+  // -------------------------------------------------------------------- consumers
   const int ctid = threadIdx.x;  // 0 … 255
+  const int nvec = p.k >> 3, nvec_pad = p.k_pad >> 3;
+  constexpr int kMaxHoist = 2;  // 16-byte pieces of the norm weight a thread keeps in registers (k ≤ 4096)
+
+  // Everything that does not depend on the producer kernel is fetched BEFORE griddepcontrol.wait: the RMSNorm weight,
+  // the bias of this CTA's first row block.
+  uint4 wn[kMaxHoist];
+  if constexpr (PRO != PRO_PLAIN) {
+    const uint4* wg = reinterpret_cast<const uint4*>(p.norm_w);
+#pragma unroll
+    for (int j = 0; j < kMaxHoist; ++j) {
+      const int i = ctid + j * kConsumers;
+      wn[j] = (i < nvec) ? wg[i] : make_uint4(0, 0, 0, 0);
+    }
+  }
+  const int my_row0 = (int)blockIdx.x * kBoxR + warp * RPW + ((lane < RPW) ? lane : 0);
+  __nv_bfloat16 bias_v = f_to_bf16(0.f);
+  if constexpr (EPI == EPI_PLAIN) {
+    if (p.bias != nullptr && lane < RPW && my_rbs > 0 && my_row0 < p.n) bias_v = p.bias[my_row0];
+  }
+
+  pdl_wait();  // the producer kernel's output (x, residual) is complete and visible from here on
 
   if constexpr (PRO == PRO_PLAIN) {
     const uint4* xg = reinterpret_cast<const uint4*>(p.x);
     uint4* xv = reinterpret_cast<uint4*>(xs);
-    const int nvec = p.k >> 3, nvec_pad = p.k_pad >> 3;
     for (int i = ctid; i < nvec_pad; i += kConsumers) xv[i] = (i < nvec) ? xg[i] : make_uint4(0, 0, 0, 0);
   } else {
     // hidden vector h (k elements): either x itself, or residual + Σ_r partial_r (tensor parallel)
-    const int nvec = p.k >> 3, nvec_pad = p.k_pad >> 3;
     float ss = 0.f;
+    uint4 xr[kMaxHoist];
     if constexpr (PRO == PRO_TP_RMSNORM) {
       if (ctid == 0) {
         const unsigned long long want = (*p.tp_epoch + 1ull) * (unsigned long long)p.tp_arrivals;
@@ -133,11 +152,20 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
       }
     } else {
       const uint4* xg = reinterpret_cast<const uint4*>(p.x);
-      for (int i = ctid; i < nvec; i += kConsumers) {
+#pragma unroll
+      for (int j = 0; j < kMaxHoist; ++j) {
+        const int i = ctid + j * kConsumers;
+        xr[j] = (i < nvec) ? xg[i] : make_uint4(0, 0, 0, 0);
+        float xf[8];
+        unpack8(xr[j], xf);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ss += xf[e] * xf[e];
+      }
+      for (int i = ctid + kMaxHoist * kConsumers; i < nvec; i += kConsumers) {
         float xf[8];
         unpack8(xg[i], xf);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) ss += xf[j] * xf[j];
+        for (int e = 0; e < 8; ++e) ss += xf[e] * xf[e];
       }
     }
     ss = warp_sum(ss);
@@ -149,21 +177,36 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
     const float inv = rsqrtf(tot / (float)p.k + p.eps);
     const uint4* wg = reinterpret_cast<const uint4*>(p.norm_w);
     uint4* xv = reinterpret_cast<uint4*>(xs);
-    for (int i = ctid; i < nvec_pad; i += kConsumers) {
+    auto scale = [&](const uint4& xq, const uint4& wq) {
+      float xf[8], wf[8];
+      unpack8(xq, xf);
+      unpack8(wq, wf);
+      uint4 o;  // reference order: normed = x * inv; normed *= w; round once
+      o.x = pack2(xf[0] * inv * wf[0], xf[1] * inv * wf[1]);
+      o.y = pack2(xf[2] * inv * wf[2], xf[3] * inv * wf[3]);
+      o.z = pack2(xf[4] * inv * wf[4], xf[5] * inv * wf[5]);
+      o.w = pack2(xf[6] * inv * wf[6], xf[7] * inv * wf[7]);
+      return o;
+    };
+#pragma unroll
+    for (int j = 0; j < kMaxHoist; ++j) {
+      const int i = ctid + j * kConsumers;
+      if (i < nvec_pad) {
+        if constexpr (PRO == PRO_TP_RMSNORM) {
+          xv[i] = (i < nvec) ? scale(xv[i], wn[j]) : make_uint4(0, 0, 0, 0);
+        } else {
+          xv[i] = (i < nvec) ? scale(xr[j], wn[j]) : make_uint4(0, 0, 0, 0);
+        }
+      }
+    }
+    for (int i = ctid + kMaxHoist * kConsumers; i < nvec_pad; i += kConsumers) {
       uint4 o = make_uint4(0, 0, 0, 0);
       if (i < nvec) {
-        float xf[8], wf[8];
         if constexpr (PRO == PRO_TP_RMSNORM) {
-          unpack8(xv[i], xf);
+          o = scale(xv[i], wg[i]);
         } else {
-          unpack8(reinterpret_cast<const uint4*>(p.x)[i], xf);
+          o = scale(reinterpret_cast<const uint4*>(p.x)[i], wg[i]);
         }
-        unpack8(wg[i], wf);
-        // reference order: normed = x * inv; normed *= w; round once
-        o.x = pack2(xf[0] * inv * wf[0], xf[1] * inv * wf[1]);
-        o.y = pack2(xf[2] * inv * wf[2], xf[3] * inv * wf[3]);
-        o.z = pack2(xf[4] * inv * wf[4], xf[5] * inv * wf[5]);
-        o.w = pack2(xf[6] * inv * wf[6], xf[7] * inv * wf[7]);
       }
       xv[i] = o;
     }
@@ -175,6 +218,16 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
   uint32_t ph = 0;
   const uint8_t* const my_rows = stage_base + (size_t)(warp * RPW) * kRowBytes + lane * 16;
   for (int i = 0; i < my_rbs; ++i) {
+    const int row_base = ((int)blockIdx.x + i * (int)gridDim.x) * kBoxR + warp * RPW;
+    // operands of the epilogue are requested now so that their latency hides behind the k loop
+    __nv_bfloat16 res_v = f_to_bf16(0.f);
+    if constexpr (EPI == EPI_RESIDUAL) {
+      if (lane < RPW && row_base + lane < p.n) res_v = p.residual[row_base + lane];
+    }
+    if constexpr (EPI == EPI_PLAIN) {
+      if (i > 0 && p.bias != nullptr && lane < RPW && row_base + lane < p.n) bias_v = p.bias[row_base + lane];
+    }
+
     float acc[NSEG][RPW];
 #pragma unroll
     for (int seg = 0; seg < NSEG; ++seg)
@@ -210,24 +263,29 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
 #pragma unroll
       for (int r = 0; r < RPW; ++r) acc[seg][r] = warp_sum(acc[seg][r]);
 
-    const int row_base = ((int)blockIdx.x + i * (int)gridDim.x) * kBoxR + warp * RPW;
+    // lane r finishes row r of this warp
+    float a0 = acc[0][0], a1 = acc[NSEG - 1][0];
 #pragma unroll
-    for (int r = 0; r < RPW; ++r) {
-      const int row = row_base + r;
-      if (lane == r && row < p.n) {
-        if constexpr (EPI == EPI_PLAIN) {
-          __nv_bfloat16 v = f_to_bf16(acc[0][r]);
-          if (p.bias != nullptr) v = __hadd(v, p.bias[row]);
-          p.y[row] = v;
-        } else if constexpr (EPI == EPI_RESIDUAL) {
-          p.y[row] = __hadd(p.residual[row], f_to_bf16(acc[0][r]));
-        } else if constexpr (EPI == EPI_SILU_MUL) {
-          const float g = round_bf16(acc[0][r]);
-          const __nv_bfloat16 sg = f_to_bf16(g / (1.f + expf(-g)));
-          p.y[row] = __hmul(sg, f_to_bf16(acc[NSEG - 1][r]));
-        } else {  // EPI_TP_PUSH
-          for (int q = 0; q < p.tp_world; ++q) p.tp_push[q][row] = acc[0][r];
-        }
+    for (int r = 1; r < RPW; ++r) {
+      if (lane == r) {
+        a0 = acc[0][r];
+        a1 = acc[NSEG - 1][r];
+      }
+    }
+    const int row = row_base + lane;
+    if (lane < RPW && row < p.n) {
+      if constexpr (EPI == EPI_PLAIN) {
+        __nv_bfloat16 v = f_to_bf16(a0);
+        if (p.bias != nullptr) v = __hadd(v, bias_v);
+        p.y[row] = v;
+      } else if constexpr (EPI == EPI_RESIDUAL) {
+        p.y[row] = __hadd(res_v, f_to_bf16(a0));
+      } else if constexpr (EPI == EPI_SILU_MUL) {
+        const float g = round_bf16(a0);
+        const __nv_bfloat16 sg = f_to_bf16(g / (1.f + expf(-g)));
+        p.y[row] = __hmul(sg, f_to_bf16(a1));
+      } else {  // EPI_TP_PUSH
+        for (int q = 0; q < p.tp_world; ++q) p.tp_push[q][row] = a0;
       }
     }
   }

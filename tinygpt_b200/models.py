@@ -77,13 +77,15 @@ QWEN3_17B = ModelSpec("Qwen3-1.7B", "qwen3", 2048, 28, 16, 8, 128, 6144, 151936,
 MISTRAL_7B = ModelSpec("Mistral-7B-v0.3", "mistral", 4096, 32, 32, 8, 128, 14336, 32768, 1e6, 1e-5, tie=False)
 
 # Small shapes for CPU-oracle parity (same code paths: bias / qk-norm / llama3 scaling / GQA group sizes 7,3,2,4).
-TINY_QWEN2 = ModelSpec("tiny-qwen2", "qwen2", 128, 2, 14, 2, 64, 256, 512, 1e6, 1e-6, tie=True, qkv_bias=True,
+# Llama, Qwen2 and Mistral derive head_dim = hidden / heads in the reference (src/model/ModelQwen2.h:20,
+# ModelLlama.h:37), so hidden = q_heads * head_dim there; Qwen3 carries an explicit head_dim.
+TINY_QWEN2 = ModelSpec("tiny-qwen2", "qwen2", 896, 2, 14, 2, 64, 256, 512, 1e6, 1e-6, tie=True, qkv_bias=True,
                        max_ctx=256)
-TINY_LLAMA = ModelSpec("tiny-llama", "llama", 256, 2, 6, 2, 128, 512, 640, 5e5, 1e-5, tie=True, max_ctx=256,
+TINY_LLAMA = ModelSpec("tiny-llama", "llama", 768, 2, 6, 2, 128, 512, 640, 5e5, 1e-5, tie=True, max_ctx=256,
                        rope_scaling=RopeScaling(32.0, 4.0, 1.0, 64))
 TINY_QWEN3 = ModelSpec("tiny-qwen3", "qwen3", 192, 2, 4, 2, 128, 320, 384, 1e6, 1e-6, tie=True, qk_norm=True,
                        max_ctx=256)
-TINY_MISTRAL = ModelSpec("tiny-mistral", "mistral", 256, 2, 8, 2, 128, 448, 512, 1e6, 1e-5, tie=False, max_ctx=256)
+TINY_MISTRAL = ModelSpec("tiny-mistral", "mistral", 1024, 2, 8, 2, 128, 448, 512, 1e6, 1e-5, tie=False, max_ctx=256)
 
 SPECS: Dict[str, ModelSpec] = {s.name: s for s in
                                (QWEN25_05B, LLAMA32_3B, QWEN3_17B, MISTRAL_7B, TINY_QWEN2, TINY_LLAMA, TINY_QWEN3,
