@@ -43,9 +43,10 @@ def test_attention_tinyfa_shapes(built_lib, B, Sq, Skv, Hq, Hkv, hd, causal):
 @pytest.mark.parametrize("Hq,Hkv,hd,L", [(14, 2, 64, 144), (24, 8, 128, 240), (16, 8, 128, 31), (32, 8, 128, 129),
                                           (4, 4, 64, 1), (8, 1, 64, 500), (6, 2, 128, 17), (14, 2, 64, 257),
                                           (16, 8, 128, 512), (14, 2, 64, 256)])
-def test_attn_decode_plain(built_lib, Hq, Hkv, hd, L):
-    """pos == NULL mode: attention of one query row over `L` cached rows (no rotation, nothing appended)."""
-    max_ctx = 512
+@pytest.mark.parametrize("max_ctx", [512, 2048], ids=["cta-per-head", "cta-per-gqa-group"])
+def test_attn_decode_plain(built_lib, Hq, Hkv, hd, L, max_ctx):
+    """pos == NULL mode: attention of one query row over `L` cached rows (no rotation, nothing appended).
+    max_ctx ≤ 1024 runs one CTA per query head, longer contexts one CTA per GQA group (K/V read once)."""
     q = urand_bf16(1, 1, Hq, hd, seed=1)
     k, v = urand_bf16(1, L, Hkv, hd, seed=2), urand_bf16(1, L, Hkv, hd, seed=3)
     kc = torch.zeros(max_ctx, Hkv, hd, dtype=torch.bfloat16)
@@ -59,12 +60,13 @@ def test_attn_decode_plain(built_lib, Hq, Hkv, hd, L):
     assert bool(((got - naive).abs() <= 1e-2 + 1e-1 * naive.abs()).all())
 
 
+@pytest.mark.parametrize("max_ctx", [384, 1536], ids=["cta-per-head", "cta-per-gqa-group"])
 @pytest.mark.parametrize("Hq,Hkv,hd,qk_norm", [(14, 2, 64, False), (24, 8, 128, False), (16, 8, 128, True),
                                                (32, 8, 128, False)])
-def test_attn_decode_fused_append(built_lib, Hq, Hkv, hd, qk_norm):
+def test_attn_decode_fused_append(built_lib, Hq, Hkv, hd, qk_norm, max_ctx):
     """The engine's launch: raw qkv → [norm] → RoPE → append at *pos → attention, for several consecutive positions.
     K/V rows written to the cache must be bit-identical to the oracle's rope(k) / v (same table, ≤ 1 ulp FMA)."""
-    max_ctx, steps, start = 384, 5, 254  # crosses the 256-key (hd 64) / 128-key (hd 128) split boundaries
+    steps, start = 5, 254  # crosses the 256-key (hd 64) / 128-key (hd 128) split boundaries
     table = orc.rope_table(hd, max_ctx, 1e6)
     g = torch.Generator().manual_seed(7)
     kc = torch.zeros(max_ctx, Hkv, hd, dtype=torch.bfloat16)

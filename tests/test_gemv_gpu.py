@@ -85,7 +85,7 @@ def test_fused_layer_pieces(built_lib, spec):
     res = x.to(DEV).clone()
     got = ops.gemv_fused(a.to(DEV), Wo.to(DEV), residual=res)
     want = orc.add(x, orc.linear(a, Wo, None))
-    assert_close_bf16(got, want, 1, "o_proj+residual", atol=1e-4, frac_exact=0.98)
+    assert_close_bf16(got, want, 2, "o_proj+residual", atol=1e-4, frac_exact=0.98)  # 1 ulp of acc can be 2 ulp of the sum
     # 3. RMSNorm → gate|up → SiLU·mul
     Wgu = rand_bf16(2 * I, H, seed=17, scale=0.02)
     got = ops.gemv_fused(x.to(DEV), Wgu.to(DEV), norm_weight=nw.to(DEV), eps=spec.rms_eps, silu_mul=True)
@@ -97,7 +97,7 @@ def test_fused_layer_pieces(built_lib, spec):
     Wd = rand_bf16(H, I, seed=19, scale=0.02)
     got = ops.gemv_fused(m.to(DEV), Wd.to(DEV), residual=x.to(DEV))
     want = orc.add(x, orc.linear(m, Wd, None))
-    assert_close_bf16(got, want, 1, "down+residual", atol=1e-4, frac_exact=0.98)
+    assert_close_bf16(got, want, 2, "down+residual", atol=1e-4, frac_exact=0.98)
 
 
 def test_gemv_linearity_full_size(built_lib):

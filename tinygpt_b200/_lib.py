@@ -60,6 +60,7 @@ PROTOTYPES = {
     "b200_engine_forward": (I32, [P, P, I64, I64, P, I32, P]),
     "b200_engine_decode": (I32, [P, I64, P, P]),
     "b200_engine_last_token": (I32, [P, P, P]),
+    "b200_engine_debug_trace": (I64, [P, P, I64]),
     "b200_engine_position": (I64, [P]),
     "b200_engine_launches_per_token": (I64, [P]),
     "b200_engine_bytes_per_token": (I64, [P, I64]),

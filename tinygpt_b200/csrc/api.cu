@@ -71,7 +71,7 @@ int b200_gemv_fused_bf16(void* y, const void* x, const void* W, int64_t n, int64
 int64_t b200_attn_decode_workspace_bytes(int64_t Hq, int64_t Hkv, int64_t hd, int64_t max_ctx) {
   if (Hkv <= 0 || Hq % Hkv != 0 || (hd != 64 && hd != 128) || max_ctx < 1) return -1;
   const int nsplit = b200::attn_decode_nsplit((int)hd, (int)max_ctx);
-  return b200::attn_decode_ws_floats((int)Hq, (int)Hkv, (int)hd, nsplit) * 4 + ((Hkv * 4 + 15) / 16) * 16;
+  return b200::attn_decode_ws_floats((int)Hq, (int)Hkv, (int)hd, nsplit) * 4 + ((Hq * 4 + 15) / 16) * 16;
 }
 
 int b200_attn_decode_bf16(void* out, const void* qkv, const void* q_norm, const void* k_norm, float eps,
@@ -95,7 +95,7 @@ int b200_attn_decode_bf16(void* out, const void* qkv, const void* q_norm, const 
   a.vcache = (__nv_bfloat16*)vcache;
   a.out = (__nv_bfloat16*)out;
   a.tickets = (unsigned int*)workspace;
-  a.ws = (float*)((uint8_t*)workspace + ((Hkv * 4 + 15) / 16) * 16);
+  a.ws = (float*)((uint8_t*)workspace + ((Hq * 4 + 15) / 16) * 16);
   a.Hq = (int)Hq;
   a.Hkv = (int)Hkv;
   a.nsplit = attn_decode_nsplit((int)hd, (int)max_ctx);

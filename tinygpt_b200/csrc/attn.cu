@@ -68,8 +68,16 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnDec
   __shared__ bool is_last;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int kvh = blockIdx.y, split = blockIdx.x;
+  // CTA = (KV split, group of G query heads that share one KV head).  G == Hq/Hkv: K/V read once per KV head (long
+  // contexts); G == 1: one CTA per query head, K/V re-read from L2 but Hq CTAs share the latency-bound work (short
+  // contexts).  `hg` indexes the head group, `kvh` its KV head; only the first group of a KV head appends the new row.
+  const int hg = blockIdx.y, split = blockIdx.x;
+  const int h0 = hg * G;
+  const int group = p.Hq / p.Hkv;
+  const int kvh = h0 / group;
+  const bool kv_leader = (h0 % group) == 0;
 
+  if (p.trace != nullptr && hg == 0 && split == 0 && tid == 0) p.trace[0] = global_timer_ns();
   pdl_trigger();
   // *p.pos was written by the PREVIOUS token's last kernel (or by reset/seek), i.e. before this graph launch began, so
   // it may be read ahead of griddepcontrol.wait — and with it every cached K/V row below pos.
@@ -109,6 +117,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnDec
   }
 
   pdl_wait();  // qkv of this token is complete and visible from here on
+  if (p.trace != nullptr && hg == 0 && split == 0 && tid == 0) p.trace[1] = global_timer_ns();
 
   const int qdim = p.Hq * HD, kvdim = p.Hkv * HD;
   const bool owns_new = append && (pos >= start) && (pos < end);
@@ -117,7 +126,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnDec
   for (int h = warp; h < G + 1; h += kAttnWarps) {
     const bool is_k = (h == G);
     if (is_k && !owns_new) break;
-    const __nv_bfloat16* src = is_k ? p.qkv + qdim + kvh * HD : p.qkv + (kvh * G + h) * HD;
+    const __nv_bfloat16* src = is_k ? p.qkv + qdim + kvh * HD : p.qkv + (h0 + h) * HD;
     const __nv_bfloat16* nw = is_k ? p.k_norm : p.q_norm;
     float x[EPL];
 #pragma unroll
@@ -151,8 +160,10 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnDec
         const __nv_bfloat16 vv = p.qkv[qdim + kvdim + kvh * HD + lane + 32 * j];
         krow[lane + 32 * j] = kk;
         vrow[lane + 32 * j] = vv;
-        kg[lane + 32 * j] = kk;
-        vg[lane + 32 * j] = vv;
+        if (kv_leader) {
+          kg[lane + 32 * j] = kk;
+          vg[lane + 32 * j] = vv;
+        }
       }
     } else {
 #pragma unroll
@@ -245,7 +256,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnDec
   }
   __syncthreads();
 
-  float* ws_base = p.ws + ((size_t)kvh * p.nsplit) * G * (HD + 2);
+  if (p.trace != nullptr && hg == 0 && split == 0 && tid == 0) p.trace[2] = global_timer_ns();
+  float* ws_base = p.ws + ((size_t)hg * p.nsplit) * G * (HD + 2);
   for (int idx = tid; idx < G * HD; idx += kAttnThreads) {
     float o = 0.f;
 #pragma unroll
@@ -253,7 +265,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnDec
     const int g = idx / HD, d = idx % HD;
     if (nact == 1) {
       const float l = ml[g * 2 + 1];
-      p.out[(kvh * G + g) * HD + d] = f_to_bf16(o * (l > 0.f ? 1.f / l : 0.f));
+      p.out[(h0 + g) * HD + d] = f_to_bf16(o * (l > 0.f ? 1.f / l : 0.f));
     } else {
       ws_base[((size_t)split * G + g) * (HD + 2) + d] = o;
     }
@@ -266,7 +278,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnDec
   __threadfence();
   __syncthreads();
   if (tid == 0) {
-    const unsigned int t = atomicAdd(&p.tickets[kvh], 1u);
+    const unsigned int t = atomicAdd(&p.tickets[hg], 1u);
     is_last = (t == (unsigned int)nact - 1);
   }
   __syncthreads();
@@ -285,9 +297,9 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnDec
       num = fmaf(w, __ldcg(&r[d]), num);
       den = fmaf(w, __ldcg(&r[HD + 1]), den);
     }
-    p.out[(kvh * G + g) * HD + d] = f_to_bf16(num * (den > 0.f ? 1.f / den : 0.f));
+    p.out[(h0 + g) * HD + d] = f_to_bf16(num * (den > 0.f ? 1.f / den : 0.f));
   }
-  if (tid == 0) p.tickets[kvh] = 0;
+  if (tid == 0) p.tickets[hg] = 0;
 }
 
 using AttnFn = void (*)(const AttnDecodeParams);
@@ -370,8 +382,12 @@ __global__ void __launch_bounds__(128) attn_general_kernel(__nv_bfloat16* __rest
 }  // namespace
 
 int64_t attn_decode_ws_floats(int Hq, int Hkv, int hd, int nsplit) {
-  return (int64_t)Hkv * nsplit * (Hq / Hkv) * (hd + 2);
+  (void)Hkv;
+  return (int64_t)Hq * nsplit * (hd + 2);  // same size whatever the head grouping
 }
+
+// Query heads per CTA: the whole GQA group once the context is long enough for K/V re-reads to matter, else one.
+int attn_heads_per_cta(int Hq, int Hkv, int max_ctx) { return (max_ctx > 1024) ? Hq / Hkv : 1; }
 
 int attn_setup_attributes() {
   static std::once_flag once;
@@ -404,10 +420,11 @@ int attn_decode_nsplit(int hd, int max_ctx) {
 int launch_attn_decode(const AttnDecodeParams& p, int hd, cudaStream_t st, bool pdl) {
   B200_CHECK_ARG(hd == 64 || hd == 128, "attention: head_dim %d not built (64 and 128 are, like the reference)", hd);
   B200_CHECK_ARG(p.Hkv > 0 && p.Hq % p.Hkv == 0, "attention: Hq=%d must be a multiple of Hkv=%d", p.Hq, p.Hkv);
-  const int G = p.Hq / p.Hkv;
+  const int G = p.heads_per_cta > 0 ? p.heads_per_cta : attn_heads_per_cta(p.Hq, p.Hkv, p.max_ctx);
+  B200_CHECK_ARG((p.Hq / p.Hkv) % G == 0, "attention: heads per CTA %d must divide the GQA group %d", G, p.Hq / p.Hkv);
   AttnFn f = (hd == 64) ? pick_attn<64>(G) : pick_attn<128>(G);
   if (!f) {
-    set_error("attention: group size Hq/Hkv=%d not built (1,2,3,4,7,8 are)", G);
+    set_error("attention: %d query heads per CTA not built (1,2,3,4,7,8 are)", G);
     return B200_ERR_UNSUPPORTED;
   }
   const int chunk = (hd == 64) ? SplitKeys<64>::value : SplitKeys<128>::value;
@@ -416,7 +433,7 @@ int launch_attn_decode(const AttnDecodeParams& p, int hd, cudaStream_t st, bool 
                  attn_decode_nsplit(hd, p.max_ctx));
   B200_CHECK_ARG(p.nsplit <= 65535, "attention: context too long");
   const size_t smem = (size_t)2 * chunk * hd * 2 + (size_t)(G * hd + kAttnWarps * G * hd + G * chunk + 2 * G) * 4;
-  B200_CUDA(launch_pdl(f, dim3(p.nsplit, p.Hkv), dim3(kAttnThreads), smem, st, pdl, p));
+  B200_CUDA(launch_pdl(f, dim3(p.nsplit, p.Hq / G), dim3(kAttnThreads), smem, st, pdl, p));
   return B200_OK;
 }
 

@@ -78,6 +78,19 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// 8 bf16 dotted with 8 fp32 values into TWO independent accumulators (even / odd elements): halves the dependent FMA
+// chain of the GEMV inner loop; the caller adds the pair once per row.
+__device__ __forceinline__ void dot8x2(const uint4& w, const float (&x)[8], float& a0, float& a1) {
+  a0 = fmaf(bf16_lo(w.x), x[0], a0);
+  a1 = fmaf(bf16_hi(w.x), x[1], a1);
+  a0 = fmaf(bf16_lo(w.y), x[2], a0);
+  a1 = fmaf(bf16_hi(w.y), x[3], a1);
+  a0 = fmaf(bf16_lo(w.z), x[4], a0);
+  a1 = fmaf(bf16_hi(w.z), x[5], a1);
+  a0 = fmaf(bf16_lo(w.w), x[6], a0);
+  a1 = fmaf(bf16_hi(w.w), x[7], a1);
+}
+
 // 8 bf16 (one 16-byte vector) dotted with 8 fp32 values
 __device__ __forceinline__ float dot8(const uint4& w, const float (&x)[8], float acc) {
   acc = fmaf(bf16_lo(w.x), x[0], acc);
@@ -145,6 +158,12 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
 
 // named barrier among a subset of the CTA's warps (id 1..15)

@@ -55,6 +55,7 @@ struct b200_engine {
   int64_t h_pos = 0;
   int64_t h_gen = 0;
   int launches_per_token = 0;
+  unsigned long long* trace = nullptr;  // B200_TRACE=1: [launch][4] globaltimer stamps of the last token
   bool use_graph = true;
   bool use_pdl = true;
 };
@@ -88,9 +89,14 @@ static int engine_launch_token(b200_engine* e, cudaStream_t st, bool with_head) 
   B200_CUDA(launch_pdl(embed_step_kernel, dim3(1), dim3(128), 0, st, false, e->x, e->embed, (const int64_t*)e->cur_tok,
                        (int64_t)d.vocab, (int)d.hidden));
   const size_t kv_layer = (size_t)d.max_ctx * e->Hkv_l * d.head_dim;
+  int slot = 0;
+  auto tr = [&]() -> unsigned long long* { return e->trace ? e->trace + 4 * (slot++) : nullptr; };
   for (int l = 0; l < d.layers; ++l) {
-    if ((rc = gemv_launch(e->p_qkv[l], st, pdl)) != B200_OK) return rc;
+    GemvPlan q = e->p_qkv[l];
+    q.p.trace = tr();
+    if ((rc = gemv_launch(q, st, pdl)) != B200_OK) return rc;
     AttnDecodeParams a{};
+    a.trace = tr();
     a.qkv = e->qkv;
     a.q_norm = (const __nv_bfloat16*)e->lw[l].q_norm;
     a.k_norm = (const __nv_bfloat16*)e->lw[l].k_norm;
@@ -108,15 +114,21 @@ static int engine_launch_token(b200_engine* e, cudaStream_t st, bool with_head) 
     a.nsplit = e->nsplit;
     a.max_ctx = d.max_ctx;
     if ((rc = launch_attn_decode(a, d.head_dim, st, pdl)) != B200_OK) return rc;
-    if ((rc = gemv_launch(e->p_o[l], st, pdl)) != B200_OK) return rc;
-    if ((rc = gemv_launch(e->p_gu[l], st, pdl)) != B200_OK) return rc;
+    GemvPlan o = e->p_o[l], gu = e->p_gu[l];
+    o.p.trace = tr();
+    gu.p.trace = tr();
+    if ((rc = gemv_launch(o, st, pdl)) != B200_OK) return rc;
+    if ((rc = gemv_launch(gu, st, pdl)) != B200_OK) return rc;
     const bool last_node = !with_head && l == d.layers - 1;
     GemvPlan dn = e->p_down[l];
     dn.p.pos_inc = last_node ? e->pos : nullptr;  // the LAST kernel of a token advances the position
+    dn.p.trace = tr();
     if ((rc = gemv_launch(dn, st, pdl && !last_node)) != B200_OK) return rc;
   }
   if (with_head) {
-    if ((rc = gemv_launch(e->p_head, st, pdl)) != B200_OK) return rc;
+    GemvPlan hd = e->p_head;
+    hd.p.trace = tr();
+    if ((rc = gemv_launch(hd, st, pdl)) != B200_OK) return rc;
     int64_t* amax = reinterpret_cast<int64_t*>((uint8_t*)e->argmax_ws + argmax_workspace_bytes(1, e->V_l));
     ArgmaxPublish pub;
     pub.pos = e->pos;
@@ -236,6 +248,11 @@ static int engine_build(const b200_model_desc* desc, const b200_weight_table* w,
   if ((rc = attn_setup_attributes()) != B200_OK) return rc;
 
   e->nsplit = attn_decode_nsplit(d.head_dim, d.max_ctx);
+  env = std::getenv("B200_TRACE");
+  if (env && env[0] == '1') {
+    B200_CUDA(cudaMalloc((void**)&e->trace, (size_t)(5 * d.layers + 8) * 4 * 8));
+    B200_CUDA(cudaMemset(e->trace, 0, (size_t)(5 * d.layers + 8) * 4 * 8));
+  }
   e->gen_cap = 1 << 16;
 
   // ---- one arena for everything the engine owns
@@ -253,7 +270,7 @@ static int engine_build(const b200_model_desc* desc, const b200_weight_table* w,
   const size_t o_act = take((size_t)e->I_l * 2);
   const size_t o_logits = take((size_t)e->V_l * 2);
   const size_t o_ws = take((size_t)attn_decode_ws_floats(e->Hq_l, e->Hkv_l, d.head_dim, e->nsplit) * 4);
-  const size_t o_tick = take((size_t)e->Hkv_l * 4);
+  const size_t o_tick = take((size_t)e->Hq_l * 4);
   const size_t o_amax = take((size_t)argmax_workspace_bytes(1, e->V_l) + 16);
   const size_t o_tok = take(8);
   const size_t o_log = take((size_t)e->gen_cap * 8);
@@ -278,6 +295,29 @@ static int engine_build(const b200_model_desc* desc, const b200_weight_table* w,
   e->pos = (int*)(e->arena + o_pos);
   e->gen_count = (unsigned long long*)(e->arena + o_cnt);
 
+  // ---- shared-memory budgets.  PDL keeps two consecutive kernels resident on an SM, and a kernel's TMA ring is
+  // filled while its predecessors still run; the deeper the ring, the more of a layer's weights are already on chip
+  // when the dependency resolves.  Budgets are what each GEMV could use, clipped so that every consecutive pair
+  // (qkv, attn, o, gate_up, down, qkv, …) fits in one SM.
+  const int kPair = 220 * 1024;
+  const int attn_smem = 2 * (d.head_dim == 64 ? 256 : 128) * d.head_dim * 2 + 40 * 1024;
+  const int nqkv_rows = e->qdim + 2 * e->kvdim;
+  int want_qkv = gemv_smem_wanted(nqkv_rows, d.hidden, 1, e->num_sms);
+  int want_o = gemv_smem_wanted(d.hidden, e->qdim, 1, e->num_sms);
+  int want_gu = gemv_smem_wanted(e->I_l, d.hidden, 2, e->num_sms);
+  int want_dn = gemv_smem_wanted(d.hidden, e->I_l, 1, e->num_sms);
+  int b_qkv = std::min(want_qkv, kPair - attn_smem);
+  int b_o = std::min(want_o, kPair - attn_smem);
+  int b_gu = want_gu, b_dn = want_dn;
+  if (b_gu + b_dn > kPair) {  // split what the pair has in proportion to what each wants
+    b_gu = (int)((int64_t)kPair * want_gu / (want_gu + want_dn));
+    b_dn = kPair - b_gu;
+  }
+  b_gu = std::min(b_gu, kPair - b_o);
+  b_dn = std::min(b_dn, kPair - b_qkv);
+  const int b_head = std::min(kGemvMaxSmem, kPair - b_dn);
+  if (std::getenv("B200_UNIFORM_SMEM")) b_qkv = b_o = b_gu = b_dn = kGemvDefaultSmem;
+
   // ---- GEMV plans (TMA descriptors are encoded once, here)
   e->p_qkv.resize(d.layers);
   e->p_o.resize(d.layers);
@@ -287,7 +327,8 @@ static int engine_build(const b200_model_desc* desc, const b200_weight_table* w,
   for (int l = 0; l < d.layers; ++l) {
     const b200_layer_weights& lw = e->lw[l];
     GemvPlan& q = e->p_qkv[l];
-    if ((rc = gemv_make_plan(&q, lw.qkv_w, nqkv, nqkv, d.hidden, 1, PRO_RMSNORM, EPI_PLAIN, e->num_sms)) != B200_OK)
+    if ((rc = gemv_make_plan(&q, lw.qkv_w, nqkv, nqkv, d.hidden, 1, PRO_RMSNORM, EPI_PLAIN, e->num_sms, b_qkv)) !=
+        B200_OK)
       return rc;
     q.p.x = e->x;
     q.p.norm_w = (const __nv_bfloat16*)lw.input_norm;
@@ -296,7 +337,7 @@ static int engine_build(const b200_model_desc* desc, const b200_weight_table* w,
     q.p.y = e->qkv;
 
     GemvPlan& o = e->p_o[l];
-    if ((rc = gemv_make_plan(&o, lw.o_w, d.hidden, d.hidden, e->qdim, 1, PRO_PLAIN, EPI_RESIDUAL, e->num_sms)) !=
+    if ((rc = gemv_make_plan(&o, lw.o_w, d.hidden, d.hidden, e->qdim, 1, PRO_PLAIN, EPI_RESIDUAL, e->num_sms, b_o)) !=
         B200_OK)
       return rc;
     o.p.x = e->attn;
@@ -305,7 +346,7 @@ static int engine_build(const b200_model_desc* desc, const b200_weight_table* w,
 
     GemvPlan& g = e->p_gu[l];
     if ((rc = gemv_make_plan(&g, lw.gate_up_w, 2 * (int64_t)e->I_l, e->I_l, d.hidden, 2, PRO_RMSNORM, EPI_SILU_MUL,
-                             e->num_sms)) != B200_OK)
+                             e->num_sms, b_gu)) != B200_OK)
       return rc;
     g.p.x = e->x;
     g.p.norm_w = (const __nv_bfloat16*)lw.post_norm;
@@ -313,14 +354,15 @@ static int engine_build(const b200_model_desc* desc, const b200_weight_table* w,
     g.p.y = e->act;
 
     GemvPlan& dn = e->p_down[l];
-    if ((rc = gemv_make_plan(&dn, lw.down_w, d.hidden, d.hidden, e->I_l, 1, PRO_PLAIN, EPI_RESIDUAL, e->num_sms)) !=
+    if ((rc = gemv_make_plan(&dn, lw.down_w, d.hidden, d.hidden, e->I_l, 1, PRO_PLAIN, EPI_RESIDUAL, e->num_sms, b_dn)) !=
         B200_OK)
       return rc;
     dn.p.x = e->act;
     dn.p.residual = e->x;
     dn.p.y = e->x;
   }
-  if ((rc = gemv_make_plan(&e->p_head, w->lm_head, e->V_l, e->V_l, d.hidden, 1, PRO_RMSNORM, EPI_PLAIN, e->num_sms)) !=
+  if ((rc = gemv_make_plan(&e->p_head, w->lm_head, e->V_l, e->V_l, d.hidden, 1, PRO_RMSNORM, EPI_PLAIN, e->num_sms,
+                           b_head)) !=
       B200_OK)
     return rc;
   e->p_head.p.x = e->x;
@@ -352,6 +394,7 @@ void b200_engine_destroy(b200_engine* e) {
   if (e->g_step) cudaGraphExecDestroy(e->g_step);
   if (e->g_body) cudaGraphExecDestroy(e->g_body);
   if (e->arena) cudaFree(e->arena);
+  if (e->trace) cudaFree(e->trace);
   delete e;
 }
 
@@ -443,6 +486,13 @@ int b200_engine_last_token(b200_engine* e, int64_t* token_out, void* stream) {
 }
 
 int64_t b200_engine_position(const b200_engine* e) { return e ? e->h_pos : -1; }
+
+int64_t b200_engine_debug_trace(b200_engine* e, uint64_t* out_host, int64_t max_entries) {
+  if (!e || !e->trace || !out_host) return 0;
+  const int64_t n = std::min<int64_t>(max_entries, 5 * e->d.layers + 1);
+  if (cudaMemcpy(out_host, e->trace, (size_t)n * 4 * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return n;
+}
 int64_t b200_engine_launches_per_token(const b200_engine* e) { return e ? e->launches_per_token : -1; }
 
 int64_t b200_engine_bytes_per_token(const b200_engine* e, int64_t ctx) {

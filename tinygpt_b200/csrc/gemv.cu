@@ -36,8 +36,11 @@ constexpr int kThreads = (kNW + 1) * 32;    // + 1 producer warp
 constexpr int kBoxK = 256;                  // columns per TMA box
 constexpr int kRowBytes = kBoxK * 2;        // 512
 constexpr int kConsumers = kNW * 32;
-constexpr int kSmemBudget = 100 * 1024;     // ≤ half an SM so that two PDL-overlapped kernels co-reside
 constexpr int kMaxStages = 32;
+
+// 256-column TMA boxes per pipeline stage: every stage carries 16 KB (32 KB for RPW 4 × 2 segments) so that the
+// per-stage barrier traffic is amortised whatever the row-block height.
+__host__ __device__ constexpr int kboxes(int rpw, int nseg) { return (4 / (rpw * nseg)) > 0 ? 4 / (rpw * nseg) : 1; }
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
   unsigned long long v;
@@ -52,7 +55,9 @@ template <int RPW, int NSEG, int PRO, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap) {
   constexpr int kBoxR = kNW * RPW;
-  constexpr int kStageBytes = NSEG * kBoxR * kRowBytes;
+  constexpr int KB = kboxes(RPW, NSEG);                 // 256-column boxes per stage (stage = 16 KB, 32 KB for 4×2)
+  constexpr int kBoxBytes = kBoxR * kRowBytes;
+  constexpr int kStageBytes = KB * NSEG * kBoxBytes;
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* const stage_base = smem;
@@ -63,9 +68,10 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int ksteps = p.k_pad / kBoxK;
+  const int ksteps = p.k_pad / (kBoxK * KB);
   const int my_rbs = (p.rowblocks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
+  if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[0] = global_timer_ns();
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full[s], 1);
@@ -89,8 +95,11 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
           mbar_arrive_expect_tx(&full[s], kStageBytes);
           uint8_t* dst = stage_base + (size_t)s * kStageBytes;
 #pragma unroll
-          for (int seg = 0; seg < NSEG; ++seg)
-            tma_load_2d(dst + seg * kBoxR * kRowBytes, &tmap, ks * kBoxK, seg * p.seg_rows + row0, &full[s]);
+          for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+            for (int seg = 0; seg < NSEG; ++seg)
+              tma_load_2d(dst + (kb * NSEG + seg) * kBoxBytes, &tmap, (ks * KB + kb) * kBoxK,
+                          seg * p.seg_rows + row0, &full[s]);
           if (++s == p.stages) {
             s = 0;
             ph ^= 1;
@@ -124,6 +133,7 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
   }
 
   pdl_wait();  // the producer kernel's output (x, residual) is complete and visible from here on
+  if (p.trace != nullptr && blockIdx.x == 0 && ctid == 0) p.trace[1] = global_timer_ns();
 
   if constexpr (PRO == PRO_PLAIN) {
     const uint4* xg = reinterpret_cast<const uint4*>(p.x);
@@ -228,28 +238,36 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
       if (i > 0 && p.bias != nullptr && lane < RPW && row_base + lane < p.n) bias_v = p.bias[row_base + lane];
     }
 
-    float acc[NSEG][RPW];
+    float acc[NSEG][RPW], acc_b[NSEG][RPW];
 #pragma unroll
     for (int seg = 0; seg < NSEG; ++seg)
 #pragma unroll
-      for (int r = 0; r < RPW; ++r) acc[seg][r] = 0.f;
+      for (int r = 0; r < RPW; ++r) acc[seg][r] = acc_b[seg][r] = 0.f;
 
     for (int ks = 0; ks < ksteps; ++ks) {
-      const uint4 xvv = *reinterpret_cast<const uint4*>(xs + ks * kBoxK + lane * 8);
-      float xf[8];
-      unpack8(xvv, xf);
+      uint4 xq[KB];
+#pragma unroll
+      for (int kb = 0; kb < KB; ++kb)
+        xq[kb] = *reinterpret_cast<const uint4*>(xs + (ks * KB + kb) * kBoxK + lane * 8);
       mbar_wait(&full[s], ph);
       const uint8_t* st = my_rows + (size_t)s * kStageBytes;
-      uint4 wv[NSEG][RPW];
+      uint4 wv[KB][NSEG][RPW];
 #pragma unroll
-      for (int seg = 0; seg < NSEG; ++seg)
+      for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
-        for (int r = 0; r < RPW; ++r)
-          wv[seg][r] = *reinterpret_cast<const uint4*>(st + (seg * kBoxR + r) * kRowBytes);
+        for (int seg = 0; seg < NSEG; ++seg)
 #pragma unroll
-      for (int seg = 0; seg < NSEG; ++seg)
+          for (int r = 0; r < RPW; ++r)
+            wv[kb][seg][r] = *reinterpret_cast<const uint4*>(st + (kb * NSEG + seg) * kBoxBytes + r * kRowBytes);
 #pragma unroll
-        for (int r = 0; r < RPW; ++r) acc[seg][r] = dot8(wv[seg][r], xf, acc[seg][r]);
+      for (int kb = 0; kb < KB; ++kb) {
+        float xf[8];
+        unpack8(xq[kb], xf);
+#pragma unroll
+        for (int seg = 0; seg < NSEG; ++seg)
+#pragma unroll
+          for (int r = 0; r < RPW; ++r) dot8x2(wv[kb][seg][r], xf, acc[seg][r], acc_b[seg][r]);
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
       if (++s == p.stages) {
@@ -261,7 +279,7 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
 #pragma unroll
     for (int seg = 0; seg < NSEG; ++seg)
 #pragma unroll
-      for (int r = 0; r < RPW; ++r) acc[seg][r] = warp_sum(acc[seg][r]);
+      for (int r = 0; r < RPW; ++r) acc[seg][r] = warp_sum(acc[seg][r] + acc_b[seg][r]);
 
     // lane r finishes row r of this warp
     float a0 = acc[0][0], a1 = acc[NSEG - 1][0];
@@ -291,6 +309,7 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
   }
 
   if (p.pos_inc != nullptr && blockIdx.x == 0 && ctid == 0) *p.pos_inc += 1;
+  if (p.trace != nullptr && blockIdx.x == 0 && ctid == 0) p.trace[2] = global_timer_ns();
 
   if constexpr (EPI == EPI_TP_PUSH) {
     __threadfence_system();
@@ -346,7 +365,7 @@ int gemv_setup_attributes() {
           for (int epi = 0; epi < 4; ++epi) {
             KernelFn f = pick(rpw, nseg, pro, epi);
             if (!f) continue;
-            cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 4096);
+            cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemvMaxSmem + 4096);
             // one carveout for every kernel of the token: a change of carveout between launches drains the SM and
             // would serialise the PDL overlap
             if (e == cudaSuccess)
@@ -363,16 +382,13 @@ int gemv_setup_attributes() {
   return rc;
 }
 
-int gemv_make_plan(GemvPlan* plan, const void* W, int64_t rows_total, int64_t n, int64_t k, int nseg, int pro, int epi,
-                   int num_sms) {
-  B200_CHECK_ARG(W != nullptr && n > 0 && k > 0, "gemv: null weight or empty shape (n=%lld k=%lld)", (long long)n,
-                 (long long)k);
-  B200_CHECK_ARG(k % 8 == 0, "gemv: k=%lld must be a multiple of 8 (16-byte rows)", (long long)k);
-  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(W) & 15) == 0, "gemv: W must be 16-byte aligned");
-  B200_CHECK_ARG(nseg == 1 || nseg == 2, "gemv: nseg must be 1 or 2");
-  B200_CHECK_ARG(n < (1ll << 30) && k < (1ll << 30) && rows_total >= n * nseg, "gemv: shape out of range");
-
-  // rows per warp: maximise the share of busy SM-slots, prefer bigger boxes when within 3 %
+namespace {
+struct Shape {
+  int rpw, box_r, kb, k_pad, stage_bytes, fixed;
+  int64_t rbs;
+};
+Shape pick_shape(int64_t n, int64_t k, int nseg, int num_sms) {
+  // rows per warp: maximise the share of busy SM-slots, prefer bigger TMA boxes when within 3 %
   int best_rpw = 1;
   double best_eff = -1.0;
   const char* force = std::getenv("B200_GEMV_RPW");
@@ -388,35 +404,61 @@ int gemv_make_plan(GemvPlan* plan, const void* W, int64_t rows_total, int64_t n,
       best_rpw = rpw;
     }
   }
-  const int rpw = best_rpw;
-  const int box_r = 8 * rpw;
-  const int64_t rbs = (n + box_r - 1) / box_r;
-  const int k_pad = (int)((k + kBoxK - 1) / kBoxK * kBoxK);
-  const int stage_bytes = nseg * box_r * kRowBytes;
-  const int fixed = k_pad * 2 + 64;  // x vector + reduction scratch
-  int stages = (kSmemBudget - fixed) / (stage_bytes + 16);
-  stages = std::max(2, std::min(stages, kMaxStages));
+  Shape s;
+  s.rpw = best_rpw;
+  s.box_r = 8 * s.rpw;
+  s.rbs = (n + s.box_r - 1) / s.box_r;
+  s.kb = kboxes(s.rpw, nseg);
+  s.k_pad = (int)((k + kBoxK * s.kb - 1) / (kBoxK * s.kb) * (kBoxK * s.kb));
+  s.stage_bytes = s.kb * nseg * s.box_r * kRowBytes;
+  s.fixed = s.k_pad * 2 + 64;  // x vector + reduction scratch
+  return s;
+}
+}  // namespace
+
+int gemv_smem_wanted(int64_t n, int64_t k, int nseg, int num_sms) {
+  const Shape s = pick_shape(n, k, nseg, num_sms);
+  const int64_t g = std::min<int64_t>(s.rbs, num_sms);
+  const int64_t stages = std::min<int64_t>(kMaxStages, ((s.rbs + g - 1) / g) * (s.k_pad / (kBoxK * s.kb)));
+  return (int)std::min<int64_t>(kGemvMaxSmem, stages * (s.stage_bytes + 16) + s.fixed);
+}
+
+int gemv_make_plan(GemvPlan* plan, const void* W, int64_t rows_total, int64_t n, int64_t k, int nseg, int pro, int epi,
+                   int num_sms, int smem_budget) {
+  B200_CHECK_ARG(W != nullptr && n > 0 && k > 0, "gemv: null weight or empty shape (n=%lld k=%lld)", (long long)n,
+                 (long long)k);
+  B200_CHECK_ARG(k % 8 == 0, "gemv: k=%lld must be a multiple of 8 (16-byte rows)", (long long)k);
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(W) & 15) == 0, "gemv: W must be 16-byte aligned");
+  B200_CHECK_ARG(nseg == 1 || nseg == 2, "gemv: nseg must be 1 or 2");
+  B200_CHECK_ARG(n < (1ll << 30) && k < (1ll << 30) && rows_total >= n * nseg, "gemv: shape out of range");
+  smem_budget = std::max(32 * 1024, std::min(smem_budget, kGemvMaxSmem));
+
+  const Shape sh = pick_shape(n, k, nseg, num_sms);
+  const int64_t g = std::min<int64_t>(sh.rbs, num_sms);
+  const int64_t most = ((sh.rbs + g - 1) / g) * (sh.k_pad / (kBoxK * sh.kb));  // stages of the busiest CTA
+  int stages = (smem_budget - sh.fixed) / (sh.stage_bytes + 16);
+  stages = (int)std::max<int64_t>(2, std::min<int64_t>(std::min<int64_t>(stages, kMaxStages), std::max<int64_t>(most, 2)));
   const char* fs = std::getenv("B200_GEMV_STAGES");
   if (fs) stages = std::max(2, std::min(std::atoi(fs), kMaxStages));
 
   *plan = GemvPlan{};
-  plan->rpw = rpw;
+  plan->rpw = sh.rpw;
   plan->nseg = nseg;
   plan->pro = pro;
   plan->epi = epi;
-  plan->grid = (int)std::min<int64_t>(rbs, num_sms);
-  plan->smem = stages * stage_bytes + k_pad * 2 + stages * 16 + 64;
+  plan->grid = (int)g;
+  plan->smem = stages * sh.stage_bytes + sh.k_pad * 2 + stages * 16 + 64;
   plan->p.n = (int)n;
   plan->p.k = (int)k;
-  plan->p.k_pad = k_pad;
+  plan->p.k_pad = sh.k_pad;
   plan->p.seg_rows = (nseg == 2) ? (int)n : 0;
-  plan->p.rowblocks = (int)rbs;
+  plan->p.rowblocks = (int)sh.rbs;
   plan->p.stages = stages;
   plan->p.tp_world = 1;
-  B200_CHECK_ARG(pick(rpw, nseg, pro, epi) != nullptr, "gemv: no kernel for nseg=%d pro=%d epi=%d", nseg, pro, epi);
-  B200_CHECK_ARG(plan->smem <= kSmemBudget + 4096, "gemv: k=%lld needs %d bytes of shared memory", (long long)k,
+  B200_CHECK_ARG(pick(sh.rpw, nseg, pro, epi) != nullptr, "gemv: no kernel for nseg=%d pro=%d epi=%d", nseg, pro, epi);
+  B200_CHECK_ARG(plan->smem <= kGemvMaxSmem + 4096, "gemv: k=%lld needs %d bytes of shared memory", (long long)k,
                  plan->smem);
-  return make_tmap_2d_bf16(&plan->tmap, W, rows_total, k, box_r, kBoxK);
+  return make_tmap_2d_bf16(&plan->tmap, W, rows_total, k, sh.box_r, kBoxK);
 }
 
 int gemv_launch(const GemvPlan& plan, cudaStream_t stream, bool pdl) {

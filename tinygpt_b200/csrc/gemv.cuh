@@ -31,6 +31,7 @@ struct GemvParams {
   int seg_rows;                   // row offset of segment 1 inside W (NSEG == 2: gate rows | up rows)
   int rowblocks;                  // ceil(n / (8 * RPW))
   int stages;                     // depth of the shared-memory ring
+  unsigned long long* trace;      // debug (B200_TRACE=1): CTA 0 stores globaltimer at entry / after the PDL wait / at exit
   int* pos_inc;                   // engine: when set, CTA 0 advances the token position after its last row block
   // ---- tensor-parallel exchange (peer-mapped windows over NVLink), see tp.cuh
   float* tp_push[kMaxTpWorld];            // EPI_TP_PUSH: slot for MY partial inside rank r's window ([n] floats)
@@ -56,8 +57,14 @@ struct GemvPlan {
 };
 
 // Plan a GEMV over W[rows_total, k] (row-major bf16).  `n` = rows produced (per segment).
+// `smem_budget` bounds the dynamic shared memory of the launch (ring depth): consecutive PDL-chained kernels co-reside
+// on an SM, so the engine hands out budgets whose pairwise sums fit in 227 KB (gemv_smem_wanted tells how much a
+// kernel could use to hold ALL of its busiest CTA's weights).
+constexpr int kGemvDefaultSmem = 100 * 1024;
+constexpr int kGemvMaxSmem = 200 * 1024;
 int gemv_make_plan(GemvPlan* plan, const void* W, int64_t rows_total, int64_t n, int64_t k, int nseg, int pro, int epi,
-                   int num_sms);
+                   int num_sms, int smem_budget = kGemvDefaultSmem);
+int gemv_smem_wanted(int64_t n, int64_t k, int nseg, int num_sms);
 int gemv_launch(const GemvPlan& plan, cudaStream_t stream, bool pdl);
 int gemv_setup_attributes();  // cudaFuncSetAttribute(max dynamic smem) for every instantiation, once per process
 

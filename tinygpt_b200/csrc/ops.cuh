@@ -41,11 +41,14 @@ struct AttnDecodeParams {
   __nv_bfloat16* kcache;         // [max_ctx, Hkv, hd]
   __nv_bfloat16* vcache;         // [max_ctx, Hkv, hd]
   __nv_bfloat16* out;            // [Hq*hd]
-  float* ws;                     // split partials: [Hkv][nsplit][G][hd + 2] floats
-  unsigned int* tickets;         // [Hkv], zero-initialised, self-resetting
+  float* ws;                     // split partials: [Hq / G][nsplit][G][hd + 2] floats (G = query heads per CTA)
+  unsigned int* tickets;         // [Hq], zero-initialised, self-resetting
+  int heads_per_cta;             // 0 = choose from max_ctx (attn_heads_per_cta)
+  unsigned long long* trace;     // debug timestamps (see GemvParams::trace)
   int Hq, Hkv, nsplit, max_ctx;  // nsplit = attn_decode_nsplit(hd, max_ctx): fixed 256 (hd 64) / 128 (hd 128) keys per split
 };
 int attn_decode_nsplit(int hd, int max_ctx);
+int attn_heads_per_cta(int Hq, int Hkv, int max_ctx);
 int launch_attn_decode(const AttnDecodeParams& p, int hd, cudaStream_t st, bool pdl);
 int64_t attn_decode_ws_floats(int Hq, int Hkv, int hd, int nsplit);
 int attn_setup_attributes();

@@ -1,0 +1,48 @@
+"""Per-launch timeline of one decode token from in-kernel %globaltimer stamps (B200_TRACE=1)."""
+import ctypes as C
+import os
+import sys
+
+os.environ["B200_TRACE"] = "1"
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tinygpt_b200 import engine, models  # noqa: E402
+from tinygpt_b200._lib import lib  # noqa: E402
+
+name = sys.argv[1] if len(sys.argv) > 1 else "Qwen2.5-0.5B"
+spec = models.SPECS[name].with_ctx(256)
+w = {k: v.cuda() for k, v in models.synth_weights(spec, seed=0).items()}
+eng = engine.DecodeEngine(spec, w)
+prompt = torch.randint(0, spec.vocab, (1, 16), generator=torch.Generator().manual_seed(0)).cuda()
+eng.reset_cache()
+eng.gen_next_token(prompt)
+eng.decode(64)
+torch.cuda.synchronize()
+n = 5 * spec.layers + 1
+buf = (C.c_uint64 * (4 * n))()
+got = lib().b200_engine_debug_trace(eng._h, buf, n)
+names = ["qkv", "attn", "o", "gu", "down"]
+t0 = buf[0]
+rows = []
+for i in range(got):
+    a, b, c = buf[4 * i] - t0, buf[4 * i + 1] - t0, buf[4 * i + 2] - t0
+    rows.append((names[i % 5] if i < 5 * spec.layers else "head", i // 5, a / 1e3, b / 1e3, c / 1e3))
+print(f"{name}: kernel  layer  entry_us  after_wait_us  exit_us   (wait = after_wait-entry, body = exit-after_wait)")
+for r in rows[:12] + rows[5 * 10:5 * 10 + 6] + rows[-6:]:
+    print(f"{r[0]:5s} {r[1]:3d}  {r[2]:9.2f} {r[3]:9.2f} {r[4]:9.2f}   wait {r[3]-r[2]:6.2f}  body {r[4]-r[3]:6.2f}")
+import collections
+agg = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0])
+prev_exit = None
+for r in rows:
+    a = agg[r[0]]
+    a[0] += 1
+    a[1] += r[3] - r[2]
+    a[2] += r[4] - r[3]
+    if prev_exit is not None:
+        a[3] += r[3] - prev_exit  # gap between the previous kernel's exit stamp and this kernel's wait return
+    prev_exit = r[4]
+print("avg per kernel type: wait-before-dependency, body, gap(prev exit -> my wait return)")
+for k, (c, wt, bd, gp) in agg.items():
+    print(f"  {k:5s} x{c:3d}: wait {wt/c:6.2f} us  body {bd/c:6.2f} us  gap {gp/c:6.2f} us")
+print(f"token span {rows[-1][4]:.1f} us")
