@@ -222,6 +222,7 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
     }
   }
   named_bar_sync(1, kConsumers);
+  if (p.trace != nullptr && blockIdx.x == 0 && ctid == 0) p.trace[3] = global_timer_ns();
 
   // ---------------------------------------------------------------------------------------------- main k loop
   int s = 0;
@@ -433,8 +434,11 @@ int gemv_make_plan(GemvPlan* plan, const void* W, int64_t rows_total, int64_t n,
   B200_CHECK_ARG(n < (1ll << 30) && k < (1ll << 30) && rows_total >= n * nseg, "gemv: shape out of range");
   smem_budget = std::max(32 * 1024, std::min(smem_budget, kGemvMaxSmem));
 
+  const char* cps = std::getenv("B200_GEMV_CTAS_PER_SM");
+  const int ctas_per_sm = cps ? std::max(1, std::min(4, std::atoi(cps))) : 1;
+  if (ctas_per_sm > 1) smem_budget = std::max(32 * 1024, smem_budget / ctas_per_sm);
   const Shape sh = pick_shape(n, k, nseg, num_sms);
-  const int64_t g = std::min<int64_t>(sh.rbs, num_sms);
+  const int64_t g = std::min<int64_t>(sh.rbs, (int64_t)num_sms * ctas_per_sm);
   const int64_t most = ((sh.rbs + g - 1) / g) * (sh.k_pad / (kBoxK * sh.kb));  // stages of the busiest CTA
   int stages = (smem_budget - sh.fixed) / (sh.stage_bytes + 16);
   stages = (int)std::max<int64_t>(2, std::min<int64_t>(std::min<int64_t>(stages, kMaxStages), std::max<int64_t>(most, 2)));
