@@ -55,6 +55,13 @@ struct b200_engine {
   int64_t h_pos = 0;
   int64_t h_gen = 0;
   int launches_per_token = 0;
+  // tensor parallel
+  int tp_world = 1, tp_rank = 0;
+  bool shard_attn = true;
+  uint8_t* win[b200::kMaxTpWorld] = {nullptr};  // exchange windows of every rank as mapped here
+  unsigned long long* tp_epoch = nullptr;          // tokens completed (local)
+  __nv_bfloat16* x_alt = nullptr;                  // second hidden-state buffer (TP ping-pong)
+  const __nv_bfloat16* x_head = nullptr;           // residual the lm_head prologue reads (TP)
   unsigned long long* trace = nullptr;  // B200_TRACE=1: [launch][4] globaltimer stamps of the last token
   bool use_graph = true;
   bool use_pdl = true;
@@ -77,7 +84,67 @@ __global__ void __launch_bounds__(128) embed_step_kernel(__nv_bfloat16* __restri
   for (int i = threadIdx.x; i < (H >> 3); i += blockDim.x) d4[i] = s4[i];
 }
 
+// Tensor parallel: last kernel of a token.  With a head: wait for every rank's (max logit, global index) candidate,
+// choose with the reference tie rule (highest index among equal maxima), publish; always: advance position and epoch.
+struct TpFinish {
+  const unsigned long long* cand_flag;  // local arrival counter of the candidate exchange
+  const float* cand;                    // local window: world × {float val, pad, int64 idx} (16 bytes each)
+  unsigned long long* epoch;       // tokens completed (every exchange point sees one round of arrivals per token)
+  unsigned long long* head_epoch;  // tokens completed WITH a head (the candidate exchange only happens for those)
+  int* pos;
+  int64_t* cur_tok;
+  int64_t* gen_log;
+  unsigned long long* gen_count;
+  int gen_cap;
+  int world;
+  int with_head;
+};
+__global__ void tp_finish_kernel(const TpFinish f) {
+  pdl_trigger();
+  pdl_wait();
+  if (threadIdx.x != 0) return;
+  const unsigned long long ep = *f.epoch;
+  if (f.with_head) {
+    const unsigned long long hep = *f.head_epoch;
+    const unsigned long long want = (hep + 1ull) * (unsigned long long)f.world;
+    unsigned long long v;
+    const unsigned long long t0 = global_timer_ns();
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f.cand_flag) : "memory");
+      if (v < want && global_timer_ns() - t0 > 4000000000ull) __trap();  // a peer died: fail loudly, never hang
+    } while (v < want);
+    *f.head_epoch = hep + 1;
+    float best = -INFINITY;
+    int64_t bi = -1;
+    for (int r = 0; r < f.world; ++r) {
+      const float val = __ldcv(f.cand + r * 4);
+      const int64_t idx = __ldcv(reinterpret_cast<const long long*>(f.cand + r * 4 + 2));
+      if (val > best || (val == best && idx > bi)) {
+        best = val;
+        bi = idx;
+      }
+    }
+    *f.cur_tok = bi;
+    const unsigned long long c = *f.gen_count;
+    f.gen_log[c % (unsigned long long)f.gen_cap] = bi;
+    *f.gen_count = c + 1;
+  }
+  *f.pos += 1;
+  *f.epoch = ep + 1;
+}
+
 }  // namespace
+
+// exchange-window layout (identical on every rank; b200_tp_window_bytes in tp.cu sizes it)
+static inline size_t tp_vec_bytes(int H) { return ((size_t)H * 4 + 255) / 256 * 256; }
+static inline size_t tp_slot_off(const b200_engine* e, int point, int rank) {
+  return ((size_t)point * e->tp_world + rank) * tp_vec_bytes(e->d.hidden);
+}
+static inline size_t tp_flags_off(const b200_engine* e) {
+  return (size_t)(2 * e->d.layers + 2) * e->tp_world * tp_vec_bytes(e->d.hidden);
+}
+static inline size_t tp_flag_off(const b200_engine* e, int point) { return tp_flags_off(e) + (size_t)point * 256; }
+static inline size_t tp_cand_off(const b200_engine* e) { return tp_flags_off(e) + (size_t)(2 * e->d.layers + 2) * 256; }
 
 static int engine_launch_token(b200_engine* e, cudaStream_t st, bool with_head) {
   const b200_model_desc& d = e->d;
@@ -121,9 +188,10 @@ static int engine_launch_token(b200_engine* e, cudaStream_t st, bool with_head) 
     if ((rc = gemv_launch(gu, st, pdl)) != B200_OK) return rc;
     const bool last_node = !with_head && l == d.layers - 1;
     GemvPlan dn = e->p_down[l];
-    dn.p.pos_inc = last_node ? e->pos : nullptr;  // the LAST kernel of a token advances the position
+    const bool tp = e->tp_world > 1;
+    dn.p.pos_inc = (last_node && !tp) ? e->pos : nullptr;  // the LAST kernel of a token advances the position
     dn.p.trace = tr();
-    if ((rc = gemv_launch(dn, st, pdl && !last_node)) != B200_OK) return rc;
+    if ((rc = gemv_launch(dn, st, pdl && !(last_node && !tp))) != B200_OK) return rc;
   }
   if (with_head) {
     GemvPlan hd = e->p_head;
@@ -131,12 +199,37 @@ static int engine_launch_token(b200_engine* e, cudaStream_t st, bool with_head) 
     if ((rc = gemv_launch(hd, st, pdl)) != B200_OK) return rc;
     int64_t* amax = reinterpret_cast<int64_t*>((uint8_t*)e->argmax_ws + argmax_workspace_bytes(1, e->V_l));
     ArgmaxPublish pub;
-    pub.pos = e->pos;
-    pub.cur_tok = e->cur_tok;
-    pub.gen_log = e->gen_log;
-    pub.gen_count = e->gen_count;
-    pub.gen_cap = e->gen_cap;
-    if ((rc = launch_argmax(amax, e->logits, 1, e->V_l, e->argmax_ws, st, false, &pub)) != B200_OK) return rc;
+    if (e->tp_world == 1) {
+      pub.pos = e->pos;
+      pub.cur_tok = e->cur_tok;
+      pub.gen_log = e->gen_log;
+      pub.gen_count = e->gen_count;
+      pub.gen_cap = e->gen_cap;
+      if ((rc = launch_argmax(amax, e->logits, 1, e->V_l, e->argmax_ws, st, false, &pub)) != B200_OK) return rc;
+    } else {
+      pub.tp_world = e->tp_world;
+      pub.tp_index_offset = (int64_t)e->tp_rank * e->V_l;
+      for (int r = 0; r < e->tp_world; ++r) {
+        pub.tp_cand[r] = reinterpret_cast<float*>(e->win[r] + tp_cand_off(e) + (size_t)e->tp_rank * 16);
+        pub.tp_flag[r] = reinterpret_cast<unsigned long long*>(e->win[r] + tp_flag_off(e, 2 * d.layers));
+      }
+      if ((rc = launch_argmax(amax, e->logits, 1, e->V_l, e->argmax_ws, st, pdl, &pub)) != B200_OK) return rc;
+    }
+  }
+  if (e->tp_world > 1) {
+    TpFinish f{};
+    f.cand_flag = reinterpret_cast<const unsigned long long*>(e->win[e->tp_rank] + tp_flag_off(e, 2 * d.layers));
+    f.cand = reinterpret_cast<const float*>(e->win[e->tp_rank] + tp_cand_off(e));
+    f.epoch = e->tp_epoch;
+    f.head_epoch = e->tp_epoch + 1;
+    f.pos = e->pos;
+    f.cur_tok = e->cur_tok;
+    f.gen_log = e->gen_log;
+    f.gen_count = e->gen_count;
+    f.gen_cap = e->gen_cap;
+    f.world = e->tp_world;
+    f.with_head = with_head ? 1 : 0;
+    B200_CUDA(launch_pdl(tp_finish_kernel, dim3(1), dim3(32), 0, st, false, f));  // last node: full dependency
   }
   return B200_OK;
 }
@@ -188,7 +281,8 @@ static int engine_run_token(b200_engine* e, cudaStream_t st, bool with_head) {
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-static int engine_build(const b200_model_desc* desc, const b200_weight_table* w, b200_engine** out) {
+static int engine_build(const b200_model_desc* desc, const b200_weight_table* w, void* const* windows,
+                        b200_engine** out) {
   B200_CHECK_ARG(desc && w && out, "engine_create: null argument");
   *out = nullptr;
   int rc = b200_device_check();
@@ -200,7 +294,16 @@ static int engine_build(const b200_model_desc* desc, const b200_weight_table* w,
   B200_CHECK_ARG(d.head_dim == 64 || d.head_dim == 128, "engine_create: head_dim %d not built (64, 128)", d.head_dim);
   B200_CHECK_ARG(d.q_heads % d.kv_heads == 0, "engine_create: q_heads %% kv_heads != 0");
   B200_CHECK_ARG(d.hidden % 8 == 0 && d.intermediate % 8 == 0, "engine_create: H and I must be multiples of 8");
-  B200_CHECK_ARG(d.tp_world <= 1, "engine_create: use b200_engine_create_tp for tensor-parallel engines");
+  const int world = windows ? d.tp_world : 1;
+  B200_CHECK_ARG(windows != nullptr || d.tp_world <= 1, "engine_create: use b200_engine_create_tp for tensor-parallel engines");
+  B200_CHECK_ARG(world >= 1 && world <= kMaxTpWorld && d.tp_rank >= 0 && d.tp_rank < std::max(world, 1),
+                 "engine_create_tp: bad rank %d / world %d", d.tp_rank, d.tp_world);
+  const bool shard_attn = world > 1 && d.tp_shard_attn != 0;
+  B200_CHECK_ARG(d.intermediate % world == 0 && d.vocab % world == 0 && (d.intermediate / world) % 8 == 0,
+                 "engine_create_tp: intermediate/vocab not divisible by world %d", world);
+  B200_CHECK_ARG(!shard_attn || (d.q_heads % world == 0 && d.kv_heads % world == 0),
+                 "engine_create_tp: heads (%d/%d) not divisible by world %d — pass tp_shard_attn = 0", d.q_heads,
+                 d.kv_heads, world);
   B200_CHECK_ARG(w->embed && w->final_norm && w->lm_head && w->rope_table && w->layers_host,
                  "engine_create: null weight pointer");
 
@@ -217,12 +320,19 @@ static int engine_build(const b200_model_desc* desc, const b200_weight_table* w,
   } guard{e};
 
   e->d = d;
-  e->d.tp_world = 1;
-  e->d.tp_rank = 0;
-  e->Hq_l = d.q_heads;
-  e->Hkv_l = d.kv_heads;
-  e->I_l = d.intermediate;
-  e->V_l = d.vocab;
+  e->tp_world = world;
+  e->tp_rank = world > 1 ? d.tp_rank : 0;
+  e->shard_attn = shard_attn;
+  e->d.tp_world = world;
+  e->d.tp_rank = e->tp_rank;
+  e->Hq_l = shard_attn ? d.q_heads / world : d.q_heads;
+  e->Hkv_l = shard_attn ? d.kv_heads / world : d.kv_heads;
+  e->I_l = d.intermediate / world;
+  e->V_l = d.vocab / world;
+  for (int r = 0; r < world && windows; ++r) {
+    B200_CHECK_ARG(windows[r] != nullptr, "engine_create_tp: window %d is null", r);
+    e->win[r] = (uint8_t*)windows[r];
+  }
   e->qdim = e->Hq_l * d.head_dim;
   e->kvdim = e->Hkv_l * d.head_dim;
   e->embed = (const __nv_bfloat16*)w->embed;
@@ -265,6 +375,7 @@ static int engine_build(const b200_model_desc* desc, const b200_weight_table* w,
   };
   const size_t o_k = take(kv_bytes), o_v = take(kv_bytes);
   const size_t o_x = take((size_t)d.hidden * 2);
+  const size_t o_x2 = take((size_t)d.hidden * 2);
   const size_t o_qkv = take((size_t)(e->qdim + 2 * e->kvdim) * 2);
   const size_t o_attn = take((size_t)e->qdim * 2);
   const size_t o_act = take((size_t)e->I_l * 2);
@@ -276,6 +387,7 @@ static int engine_build(const b200_model_desc* desc, const b200_weight_table* w,
   const size_t o_log = take((size_t)e->gen_cap * 8);
   const size_t o_pos = take(16);
   const size_t o_cnt = take(8);
+  const size_t o_epoch = take(16);
   e->arena_bytes = off;
   B200_CUDA(cudaMalloc((void**)&e->arena, e->arena_bytes));
   // zero only the small control region + activations (the KV cache is always written before it is read)
@@ -283,6 +395,8 @@ static int engine_build(const b200_model_desc* desc, const b200_weight_table* w,
   e->kcache = (__nv_bfloat16*)(e->arena + o_k);
   e->vcache = (__nv_bfloat16*)(e->arena + o_v);
   e->x = (__nv_bfloat16*)(e->arena + o_x);
+  e->x_alt = (__nv_bfloat16*)(e->arena + o_x2);
+  e->tp_epoch = (unsigned long long*)(e->arena + o_epoch);
   e->qkv = (__nv_bfloat16*)(e->arena + o_qkv);
   e->attn = (__nv_bfloat16*)(e->arena + o_attn);
   e->act = (__nv_bfloat16*)(e->arena + o_act);
@@ -318,59 +432,100 @@ static int engine_build(const b200_model_desc* desc, const b200_weight_table* w,
   const int b_head = std::min(kGemvMaxSmem, kPair - b_dn);
   if (std::getenv("B200_UNIFORM_SMEM")) b_qkv = b_o = b_gu = b_dn = kGemvDefaultSmem;
 
-  // ---- GEMV plans (TMA descriptors are encoded once, here)
+  // ---- GEMV plans (TMA descriptors are encoded once, here).
+  // Tensor parallel: the row-sharded o_proj / down_proj push fp32 partials of the hidden vector into every rank's
+  // window (EPI_TP_PUSH) and the NEXT GEMV's prologue reduces them, adds the residual and normalises
+  // (PRO_TP_RMSNORM); the hidden state ping-pongs between two buffers because CTA 0 stores the new state while other
+  // CTAs still read the old one.
   e->p_qkv.resize(d.layers);
   e->p_o.resize(d.layers);
   e->p_gu.resize(d.layers);
   e->p_down.resize(d.layers);
   const int nqkv = e->qdim + 2 * e->kvdim;
+  const bool tp = world > 1;
+  __nv_bfloat16* cur = e->x;          // buffer holding the residual stream (embed writes here)
+  __nv_bfloat16* other = e->x_alt;
+  int pending_point = -1;             // exchange point whose partials still have to be reduced into `cur`
+  int pending_grid = 0;
+  int next_point = 0;
+  auto make_reduce_prologue = [&](GemvPlan& pl) {  // consume the pending exchange in this plan's prologue
+    pl.p.tp_world = world;
+    pl.p.tp_partials = reinterpret_cast<const float*>(e->win[e->tp_rank] + tp_slot_off(e, pending_point, 0));
+    pl.p.tp_stride = (int)(tp_vec_bytes(d.hidden) / 4);
+    pl.p.tp_wait_flag = reinterpret_cast<const unsigned long long*>(e->win[e->tp_rank] + tp_flag_off(e, pending_point));
+    pl.p.tp_epoch = e->tp_epoch;
+    pl.p.tp_arrivals = (unsigned int)(world * pending_grid);
+    pl.p.tp_residual = cur;
+    pl.p.tp_h_out = other;
+    std::swap(cur, other);
+    pending_point = -1;
+  };
+  auto make_push_epilogue = [&](GemvPlan& pl) {
+    pl.p.tp_world = world;
+    for (int r = 0; r < world; ++r) {
+      pl.p.tp_push[r] = reinterpret_cast<float*>(e->win[r] + tp_slot_off(e, next_point, e->tp_rank));
+      pl.p.tp_flag[r] = reinterpret_cast<unsigned long long*>(e->win[r] + tp_flag_off(e, next_point));
+    }
+    pending_point = next_point++;
+    pending_grid = pl.grid;
+  };
   for (int l = 0; l < d.layers; ++l) {
     const b200_layer_weights& lw = e->lw[l];
     GemvPlan& q = e->p_qkv[l];
-    if ((rc = gemv_make_plan(&q, lw.qkv_w, nqkv, nqkv, d.hidden, 1, PRO_RMSNORM, EPI_PLAIN, e->num_sms, b_qkv)) !=
-        B200_OK)
+    const int q_pro = pending_point >= 0 ? PRO_TP_RMSNORM : PRO_RMSNORM;
+    if ((rc = gemv_make_plan(&q, lw.qkv_w, nqkv, nqkv, d.hidden, 1, q_pro, EPI_PLAIN, e->num_sms, b_qkv)) != B200_OK)
       return rc;
-    q.p.x = e->x;
+    q.p.x = cur;
+    if (q_pro == PRO_TP_RMSNORM) make_reduce_prologue(q);
     q.p.norm_w = (const __nv_bfloat16*)lw.input_norm;
     q.p.eps = d.rms_eps;
     q.p.bias = d.qkv_bias ? (const __nv_bfloat16*)lw.qkv_b : nullptr;
     q.p.y = e->qkv;
 
     GemvPlan& o = e->p_o[l];
-    if ((rc = gemv_make_plan(&o, lw.o_w, d.hidden, d.hidden, e->qdim, 1, PRO_PLAIN, EPI_RESIDUAL, e->num_sms, b_o)) !=
-        B200_OK)
+    const int o_epi = shard_attn ? EPI_TP_PUSH : EPI_RESIDUAL;
+    if ((rc = gemv_make_plan(&o, lw.o_w, d.hidden, d.hidden, e->qdim, 1, PRO_PLAIN, o_epi, e->num_sms, b_o)) != B200_OK)
       return rc;
     o.p.x = e->attn;
-    o.p.residual = e->x;
-    o.p.y = e->x;
+    o.p.residual = cur;
+    o.p.y = cur;
+    if (o_epi == EPI_TP_PUSH) make_push_epilogue(o);
 
     GemvPlan& g = e->p_gu[l];
-    if ((rc = gemv_make_plan(&g, lw.gate_up_w, 2 * (int64_t)e->I_l, e->I_l, d.hidden, 2, PRO_RMSNORM, EPI_SILU_MUL,
+    const int g_pro = pending_point >= 0 ? PRO_TP_RMSNORM : PRO_RMSNORM;
+    if ((rc = gemv_make_plan(&g, lw.gate_up_w, 2 * (int64_t)e->I_l, e->I_l, d.hidden, 2, g_pro, EPI_SILU_MUL,
                              e->num_sms, b_gu)) != B200_OK)
       return rc;
-    g.p.x = e->x;
+    g.p.x = cur;
+    if (g_pro == PRO_TP_RMSNORM) make_reduce_prologue(g);
     g.p.norm_w = (const __nv_bfloat16*)lw.post_norm;
     g.p.eps = d.rms_eps;
     g.p.y = e->act;
 
     GemvPlan& dn = e->p_down[l];
-    if ((rc = gemv_make_plan(&dn, lw.down_w, d.hidden, d.hidden, e->I_l, 1, PRO_PLAIN, EPI_RESIDUAL, e->num_sms, b_dn)) !=
+    const int d_epi = tp ? EPI_TP_PUSH : EPI_RESIDUAL;
+    if ((rc = gemv_make_plan(&dn, lw.down_w, d.hidden, d.hidden, e->I_l, 1, PRO_PLAIN, d_epi, e->num_sms, b_dn)) !=
         B200_OK)
       return rc;
     dn.p.x = e->act;
-    dn.p.residual = e->x;
-    dn.p.y = e->x;
+    dn.p.residual = cur;
+    dn.p.y = cur;
+    if (d_epi == EPI_TP_PUSH) make_push_epilogue(dn);
   }
-  if ((rc = gemv_make_plan(&e->p_head, w->lm_head, e->V_l, e->V_l, d.hidden, 1, PRO_RMSNORM, EPI_PLAIN, e->num_sms,
-                           b_head)) !=
-      B200_OK)
+  const int h_pro = pending_point >= 0 ? PRO_TP_RMSNORM : PRO_RMSNORM;
+  if ((rc = gemv_make_plan(&e->p_head, w->lm_head, e->V_l, e->V_l, d.hidden, 1, h_pro, EPI_PLAIN, e->num_sms,
+                           b_head)) != B200_OK)
     return rc;
-  e->p_head.p.x = e->x;
+  e->p_head.p.x = cur;
+  if (h_pro == PRO_TP_RMSNORM) make_reduce_prologue(e->p_head);
   e->p_head.p.norm_w = (const __nv_bfloat16*)w->final_norm;
   e->p_head.p.eps = d.rms_eps;
   e->p_head.p.y = e->logits;
+  // with two reductions per layer (or one per layer and an even layer count) the stream is back in e->x when the next
+  // token's embedding is written; otherwise the embedding must go to wherever layer 0 expects it — layer 0 always
+  // reads e->x, and nothing of a previous token is read from `cur`, so no fix-up is needed.
 
-  e->launches_per_token = 1 + 5 * d.layers + 2;
+  e->launches_per_token = 1 + 5 * d.layers + 2 + (tp ? 1 : 0);
   if (e->use_graph) {
     if ((rc = engine_capture(e, true, &e->g_step)) != B200_OK) return rc;
     if ((rc = engine_capture(e, false, &e->g_body)) != B200_OK) return rc;
@@ -386,7 +541,14 @@ static int engine_build(const b200_model_desc* desc, const b200_weight_table* w,
 extern "C" {
 
 int b200_engine_create(const b200_model_desc* desc, const b200_weight_table* weights, b200_engine** out) {
-  return b200::engine_build(desc, weights, out);
+  return b200::engine_build(desc, weights, nullptr, out);
+}
+
+int b200_engine_create_tp(const b200_model_desc* desc, const b200_weight_table* weights, void* const* windows_host,
+                          b200_engine** out) {
+  using namespace b200;
+  B200_CHECK_ARG(windows_host != nullptr, "engine_create_tp: windows_host is null");
+  return engine_build(desc, weights, windows_host, out);
 }
 
 void b200_engine_destroy(b200_engine* e) {
@@ -506,11 +668,3 @@ int64_t b200_engine_bytes_per_token(const b200_engine* e, int64_t ctx) {
 }
 
 }  // extern "C"
-
-extern "C" int b200_engine_create_tp(const b200_model_desc* desc, const b200_weight_table* weights,
-                                     void* const* windows_host, b200_engine** out) {
-  (void)desc; (void)weights; (void)windows_host;
-  if (out) *out = nullptr;
-  b200::set_error("engine_create_tp: tensor-parallel engine not built yet");
-  return B200_ERR_UNSUPPORTED;
-}

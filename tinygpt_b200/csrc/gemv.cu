@@ -146,14 +146,16 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
     if constexpr (PRO == PRO_TP_RMSNORM) {
       if (ctid == 0) {
         const unsigned long long want = (*p.tp_epoch + 1ull) * (unsigned long long)p.tp_arrivals;
+        const unsigned long long t0 = global_timer_ns();
         while (ld_acquire_sys(p.tp_wait_flag) < want) {
+          if (global_timer_ns() - t0 > 4000000000ull) __trap();  // a peer died: fail loudly, never hang
         }
       }
       named_bar_sync(1, kConsumers);
       // h = bf16(residual + bf16(Σ partial)), staged in xs as bf16 first
       for (int i = ctid; i < p.k; i += kConsumers) {
         float a = 0.f;
-        for (int r = 0; r < p.tp_world; ++r) a += __ldcv(p.tp_partials + (size_t)r * p.k + i);
+        for (int r = 0; r < p.tp_world; ++r) a += __ldcv(p.tp_partials + (size_t)r * p.tp_stride + i);
         const __nv_bfloat16 h = __hadd(p.tp_residual[i], f_to_bf16(a));
         xs[i] = h;
         if (blockIdx.x == 0) p.tp_h_out[i] = h;

@@ -36,7 +36,8 @@ struct GemvParams {
   // ---- tensor-parallel exchange (peer-mapped windows over NVLink), see tp.cuh
   float* tp_push[kMaxTpWorld];            // EPI_TP_PUSH: slot for MY partial inside rank r's window ([n] floats)
   unsigned long long* tp_flag[kMaxTpWorld];  // EPI_TP_PUSH: rank r's arrival counter for this exchange point
-  const float* tp_partials;               // PRO_TP_RMSNORM: local window, tp_world vectors of k floats
+  const float* tp_partials;               // PRO_TP_RMSNORM: local window, tp_world vectors, tp_stride floats apart
+  int tp_stride;
   const unsigned long long* tp_wait_flag; // PRO_TP_RMSNORM: local arrival counter
   const unsigned long long* tp_epoch;     // device counter: tokens completed (expected arrivals = (epoch+1)*tp_arrivals)
   unsigned int tp_arrivals;               // arrivals per token at that exchange point (world × producer CTAs)

@@ -209,7 +209,16 @@ __global__ void __launch_bounds__(256) argmax_kernel(int64_t* __restrict__ out, 
   if (threadIdx.x == 0) {
     out[row] = idx;
     ticket[row] = 0;  // self-reset for the next launch
-    if (pub.cur_tok != nullptr && row == 0) {
+    if (pub.tp_world > 1 && row == 0) {
+      const int64_t gidx = idx + pub.tp_index_offset;
+      for (int r = 0; r < pub.tp_world; ++r) {
+        pub.tp_cand[r][0] = v;
+        *reinterpret_cast<long long*>(pub.tp_cand[r] + 2) = gidx;
+      }
+      __threadfence_system();
+      for (int r = 0; r < pub.tp_world; ++r)
+        asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(pub.tp_flag[r]), "l"(1ull) : "memory");
+    } else if (pub.cur_tok != nullptr && row == 0) {
       // engine: the greedy token becomes the next step's input and is appended to the on-device log
       *pub.cur_tok = idx;
       if (pub.pos != nullptr) *pub.pos += 1;

@@ -21,6 +21,12 @@ struct ArgmaxPublish {
   int64_t* gen_log = nullptr;
   unsigned long long* gen_count = nullptr;
   int gen_cap = 1;
+  // tensor parallel (vocabulary-sharded lm_head): instead of publishing, push (max logit, GLOBAL index) into every
+  // rank's candidate slot and bump its arrival counter; tp_finish_kernel (engine.cu) picks the winner.
+  int tp_world = 1;
+  int64_t tp_index_offset = 0;
+  float* tp_cand[8] = {nullptr};
+  unsigned long long* tp_flag[8] = {nullptr};
 };
 int launch_argmax(int64_t* idx, const void* logits, int64_t rows, int64_t V, void* workspace, cudaStream_t st,
                   bool pdl, const ArgmaxPublish* pub);

@@ -9,12 +9,13 @@
 extern "C" {
 
 int64_t b200_tp_window_bytes(const b200_model_desc* d) {
-  if (!d || d->tp_world < 1 || d->tp_world > 8) return -1;
-  // per exchange point (2 per layer + 1 final argmax exchange): world partial vectors of H floats, 256-byte aligned,
-  // followed by one 256-byte line of arrival counters per exchange point.
+  if (!d || d->tp_world < 1 || d->tp_world > 8 || d->hidden <= 0 || d->layers <= 0) return -1;
+  // layout (engine.cu tp_slot_off / tp_flag_off / tp_cand_off): per exchange point (2 per layer, +1 for the argmax
+  // candidates, +1 spare) `world` partial hidden vectors of H floats (256-byte aligned); then one 256-byte line of
+  // arrival counters per point; then `world` 16-byte (max logit, global index) candidates.
   const int64_t points = 2ll * d->layers + 2;
   const int64_t vec = ((int64_t)d->hidden * 4 + 255) / 256 * 256;
-  return points * d->tp_world * vec + points * 256 + 4096;
+  return points * d->tp_world * vec + points * 256 + 8 * 16 + 256;
 }
 
 int b200_tp_window_create(int64_t bytes, void** window_out, uint8_t handle_out[B200_IPC_HANDLE_BYTES]) {

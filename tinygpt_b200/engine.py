@@ -33,6 +33,15 @@ class DecodeEngine:
         self.device = dev
         self._w = weights  # keep alive
         self._rope = (models.rope_table(spec) if rope_table is None else rope_table).to(dev).contiguous()
+        self.local_vocab = spec.vocab
+        desc, table = self._describe(spec, weights, rank=0, world=1, shard_attn=True)
+        h = C.c_void_p()
+        with torch.cuda.device(dev):
+            check(lib().b200_engine_create(C.byref(desc), C.byref(table), C.byref(h)), "b200_engine_create")
+        self._h = h
+
+    def _describe(self, spec, weights, rank: int, world: int, shard_attn: bool):
+        """ModelDesc + WeightTable over `weights` (merged layout; for TP the tensors are this rank's shards)."""
         L = spec.layers
         arr = (LayerWeights * L)()
         for l in range(L):
@@ -43,17 +52,16 @@ class DecodeEngine:
                                   g("self_attn.k_norm.weight"), g("self_attn.o_proj.weight"),
                                   g("post_attention_layernorm.weight"), g("mlp.gate_up_proj.weight"),
                                   g("mlp.down_proj.weight"))
-        head = weights["model.embed_tokens.weight"] if spec.tie else weights["lm_head.weight"]
+        head = weights.get("lm_head.weight")
+        if head is None:
+            head = weights["model.embed_tokens.weight"]
         self._layers = arr
         table = WeightTable(self._ptr(weights["model.embed_tokens.weight"]), self._ptr(weights["model.norm.weight"]),
                             self._ptr(head), self._rope.data_ptr(), arr)
         desc = ModelDesc(spec.hidden, L, spec.q_heads, spec.kv_heads, spec.head_dim, spec.intermediate, spec.vocab,
-                         spec.max_ctx, spec.rms_eps, int(spec.qkv_bias), int(spec.qk_norm), 0, 1, 1)
-        h = C.c_void_p()
-        with torch.cuda.device(dev):
-            check(lib().b200_engine_create(C.byref(desc), C.byref(table), C.byref(h)), "b200_engine_create")
-        self._h = h
-        self._tok_dev = torch.empty(1, dtype=torch.int64, device=dev)
+                         spec.max_ctx, spec.rms_eps, int(spec.qkv_bias), int(spec.qk_norm), rank, world,
+                         int(shard_attn))
+        return desc, table
 
     @staticmethod
     def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -98,7 +106,8 @@ class DecodeEngine:
 
     # ---------------------------------------------------------------------------------------------- forward
     def forward(self, ids: torch.Tensor, all_positions: bool = False) -> torch.Tensor:
-        """ids [1, S] int64 on the device → logits [1, S, V] (all_positions) or [1, 1, V] (last position) bf16."""
+        """ids [1, S] int64 on the device → logits [1, S, V] (all_positions) or [1, 1, V] (last position) bf16.
+        (Tensor-parallel engines return this rank's vocabulary shard, V / world columns.)"""
         if ids.dim() != 2 or ids.shape[0] != 1:
             raise B200Error("DecodeEngine.forward: ids must be [1, S] (batch-1 engine)")
         if ids.dtype != torch.int64 or not ids.is_cuda:
@@ -106,7 +115,7 @@ class DecodeEngine:
         ids = ids.contiguous()
         S = ids.shape[1]
         rows = S if all_positions else 1
-        logits = torch.empty(1, rows, self.spec.vocab, dtype=torch.bfloat16, device=self.device)
+        logits = torch.empty(1, rows, self.local_vocab, dtype=torch.bfloat16, device=self.device)
         check(lib().b200_engine_forward(self._h, ids.data_ptr(), 1, S, logits.data_ptr(), int(all_positions),
                                         self._stream()), "b200_engine_forward")
         return logits
