@@ -211,9 +211,19 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     spec = models.SPECS[args.model].with_ctx(PROMPT_LEN + NEW_TOKENS + 16)
-    w = {k: v.to(dev) for k, v in models.synth_weights(spec, seed=0).items()}
-    eng = engine.DecodeEngine(spec, w)
-    prompt = torch.randint(0, spec.vocab, (1, PROMPT_LEN), generator=torch.Generator().manual_seed(rank)).to(dev)
+    tp_mode = world > 1 and args.mode == "tp"
+    w_cpu = models.synth_weights(spec, seed=0)
+    if tp_mode:
+        from tinygpt_b200 import tp
+        eng = tp.TPDecodeEngine(spec, w_cpu, rank, world, dev)
+        w = eng._w
+    else:
+        w = {k: v.to(dev) for k, v in w_cpu.items()}
+        eng = engine.DecodeEngine(spec, w)
+    del w_cpu
+    # tensor parallel: every rank decodes the SAME sequence; replicas: one independent sequence per GPU
+    prompt = torch.randint(0, spec.vocab, (1, PROMPT_LEN),
+                           generator=torch.Generator().manual_seed(0 if tp_mode else rank)).to(dev)
     stream = torch.cuda.current_stream()
 
     def barrier():
@@ -250,7 +260,8 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    tokens_total = world * args.steps * NEW_TOKENS          # replicas: one independent sequence per GPU
+    seqs = 1 if tp_mode else world                           # TP: one sequence on N GPUs; replicas: N sequences
+    tokens_total = seqs * args.steps * NEW_TOKENS
     value = tokens_total / (ms_max / 1e3)
     ms_per_token = ms_max / (args.steps * NEW_TOKENS)
 
@@ -269,7 +280,7 @@ def run_ours(args):
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * args.steps * NEW_TOKENS / float(t.item())
+    e2e_value = seqs * args.steps * NEW_TOKENS / float(t.item())
     # the host-buffer path and the resident path decode the same sequence
     assert torch.equal(host_toks, toks.cpu()), "e2e path and resident path disagree"
 
@@ -281,13 +292,13 @@ def run_ours(args):
     # ---- roofline (rank 0)
     peak, peak_src = measured_peaks()
     ctx_mid = PROMPT_LEN + NEW_TOKENS // 2
-    bytes_tok = spec.bytes_per_token(ctx_mid)
+    bytes_tok = eng.bytes_per_token(ctx_mid)                 # THIS rank's algorithmic bytes (1/N of the weights under TP)
     achieved = bytes_tok / (ms_per_token / 1e3) / 1e9
     # isolated timing of the two largest GEMV launches, live, CUDA events on the current stream; weights cycled so
     # that consecutive launches never hit L2 (lm_head 272 MB > L2; gate_up walks all layers: L × 17 MB)
     xh = torch.randn(spec.hidden, device=dev).to(torch.bfloat16)
     nw = w["model.norm.weight"]
-    head = w["model.embed_tokens.weight"] if spec.tie else w["lm_head.weight"]
+    head = w["lm_head.weight"] if "lm_head.weight" in w else w["model.embed_tokens.weight"]
     t_head = time_kernel_isolated(lambda: ops.gemv_fused(xh, head, norm_weight=nw, eps=spec.rms_eps))
     li = [0]
 
@@ -298,7 +309,8 @@ def run_ours(args):
                        norm_weight=w[f"model.layers.{l}.post_attention_layernorm.weight"], eps=spec.rms_eps,
                        silu_mul=True)
     t_gu = time_kernel_isolated(gu, iters=2 * spec.layers, warm=spec.layers)
-    head_bytes, gu_bytes = 2 * spec.vocab * spec.hidden, 2 * 2 * spec.intermediate * spec.hidden
+    head_bytes = 2 * head.shape[0] * spec.hidden
+    gu_bytes = 2 * w["model.layers.0.mlp.gate_up_proj.weight"].shape[0] * spec.hidden
     kernels = [
         {"kernel": "gemv_stream_kernel lm_head (RMSNorm prologue)", "bytes": head_bytes, "ms": t_head,
          "achieved_gbs": head_bytes / t_head / 1e6, "frac": head_bytes / t_head / 1e6 / peak},
@@ -306,10 +318,10 @@ def run_ours(args):
          "achieved_gbs": gu_bytes / t_gu / 1e6, "frac": gu_bytes / t_gu / 1e6 / peak},
     ]
     traffic = None
-    tp = ROOT / "profiles" / "traffic.json"
-    if tp.exists():
+    tpath = ROOT / "profiles" / "traffic.json"
+    if tpath.exists() and world == 1:
         try:
-            traffic = json.loads(tp.read_text()).get(spec.name)
+            traffic = json.loads(tpath.read_text()).get(spec.name)
         except Exception:
             traffic = None
 
@@ -323,11 +335,16 @@ def run_ours(args):
     line = {
         "metric": "decode tokens/sec (bf16, batch=1)", "value": value, "unit": "tokens/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
-        "ms_per_token": ms_per_token, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_token": ms_per_token, "higher_is_better": True, "scaling": "strong" if tp_mode else "weak",
+        "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{spec.name} bf16 batch=1 {NEW_TOKENS}-token greedy decode after a {PROMPT_LEN}-token prompt",
                    "step": f"seek({PROMPT_LEN - 1}) + {NEW_TOKENS} engine steps (one CUDA graph launch per token)",
-                   "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one sequence per GPU, no collective)",
+                   "parallelism": "single GPU" if world == 1 else (
+                       f"tp{world}: FFN columns + vocabulary sharded, attention heads " +
+                       ("sharded" if eng.shard_attn else "replicated (head counts do not divide)") +
+                       "; hidden-vector reductions fused into the GEMV kernels over NVLink peer memory"
+                       if tp_mode else f"{world} independent replicas (one sequence per GPU, no collective)"),
                    "l2": "weights 0.99 GB > 126 MB L2: re-streamed from HBM every token, no explicit flush"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src,
@@ -357,6 +374,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="Qwen2.5-0.5B")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="tp", choices=["tp", "replicas"],
+                    help="N > 1: tensor parallel over one sequence (default, strong scaling) or independent replicas")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

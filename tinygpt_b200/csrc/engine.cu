@@ -87,10 +87,8 @@ __global__ void __launch_bounds__(128) embed_step_kernel(__nv_bfloat16* __restri
 // Tensor parallel: last kernel of a token.  With a head: wait for every rank's (max logit, global index) candidate,
 // choose with the reference tie rule (highest index among equal maxima), publish; always: advance position and epoch.
 struct TpFinish {
-  const unsigned long long* cand_flag;  // local arrival counter of the candidate exchange
-  const float* cand;                    // local window: world × {float val, pad, int64 idx} (16 bytes each)
-  unsigned long long* epoch;       // tokens completed (every exchange point sees one round of arrivals per token)
-  unsigned long long* head_epoch;  // tokens completed WITH a head (the candidate exchange only happens for those)
+  const uint2* cand;               // local window: world × 2 words {max-logit bits, tag}, {global index, tag}
+  unsigned long long* epoch;       // tokens completed
   int* pos;
   int64_t* cur_tok;
   int64_t* gen_log;
@@ -105,20 +103,26 @@ __global__ void tp_finish_kernel(const TpFinish f) {
   if (threadIdx.x != 0) return;
   const unsigned long long ep = *f.epoch;
   if (f.with_head) {
-    const unsigned long long hep = *f.head_epoch;
-    const unsigned long long want = (hep + 1ull) * (unsigned long long)f.world;
-    unsigned long long v;
-    const unsigned long long t0 = global_timer_ns();
-    do {
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f.cand_flag) : "memory");
-      if (v < want && global_timer_ns() - t0 > 4000000000ull) __trap();  // a peer died: fail loudly, never hang
-    } while (v < want);
-    *f.head_epoch = hep + 1;
+    const unsigned int want = (unsigned int)(ep + 1ull);
     float best = -INFINITY;
     int64_t bi = -1;
     for (int r = 0; r < f.world; ++r) {
-      const float val = __ldcv(f.cand + r * 4);
-      const int64_t idx = __ldcv(reinterpret_cast<const long long*>(f.cand + r * 4 + 2));
+      const volatile uint2* c = f.cand + 2 * r;
+      uint2 a, b;
+      unsigned int spins = 0;
+      unsigned long long t0 = 0;
+      for (;;) {
+        a.x = c[0].x; a.y = c[0].y;
+        b.x = c[1].x; b.y = c[1].y;
+        if (a.y == want && b.y == want) break;
+        if ((++spins & 0x3fffu) == 0) {  // a peer died: fail loudly, never hang
+          const unsigned long long now = global_timer_ns();
+          if (t0 == 0) t0 = now;
+          if (now - t0 > 4000000000ull) __trap();
+        }
+      }
+      const float val = __uint_as_float(a.x);
+      const int64_t idx = (int64_t)b.x;
       if (val > best || (val == best && idx > bi)) {
         best = val;
         bi = idx;
@@ -136,7 +140,7 @@ __global__ void tp_finish_kernel(const TpFinish f) {
 }  // namespace
 
 // exchange-window layout (identical on every rank; b200_tp_window_bytes in tp.cu sizes it)
-static inline size_t tp_vec_bytes(int H) { return ((size_t)H * 4 + 255) / 256 * 256; }
+static inline size_t tp_vec_bytes(int H) { return ((size_t)H * 8 + 255) / 256 * 256; }  // {value, tag} words
 static inline size_t tp_slot_off(const b200_engine* e, int point, int rank) {
   return ((size_t)point * e->tp_world + rank) * tp_vec_bytes(e->d.hidden);
 }
@@ -209,19 +213,16 @@ static int engine_launch_token(b200_engine* e, cudaStream_t st, bool with_head) 
     } else {
       pub.tp_world = e->tp_world;
       pub.tp_index_offset = (int64_t)e->tp_rank * e->V_l;
-      for (int r = 0; r < e->tp_world; ++r) {
-        pub.tp_cand[r] = reinterpret_cast<float*>(e->win[r] + tp_cand_off(e) + (size_t)e->tp_rank * 16);
-        pub.tp_flag[r] = reinterpret_cast<unsigned long long*>(e->win[r] + tp_flag_off(e, 2 * d.layers));
-      }
+      pub.tp_epoch = e->tp_epoch;
+      for (int r = 0; r < e->tp_world; ++r)
+        pub.tp_cand[r] = reinterpret_cast<uint2*>(e->win[r] + tp_cand_off(e) + (size_t)e->tp_rank * 16);
       if ((rc = launch_argmax(amax, e->logits, 1, e->V_l, e->argmax_ws, st, pdl, &pub)) != B200_OK) return rc;
     }
   }
   if (e->tp_world > 1) {
     TpFinish f{};
-    f.cand_flag = reinterpret_cast<const unsigned long long*>(e->win[e->tp_rank] + tp_flag_off(e, 2 * d.layers));
-    f.cand = reinterpret_cast<const float*>(e->win[e->tp_rank] + tp_cand_off(e));
+    f.cand = reinterpret_cast<const uint2*>(e->win[e->tp_rank] + tp_cand_off(e));
     f.epoch = e->tp_epoch;
-    f.head_epoch = e->tp_epoch + 1;
     f.pos = e->pos;
     f.cur_tok = e->cur_tok;
     f.gen_log = e->gen_log;
@@ -446,15 +447,12 @@ static int engine_build(const b200_model_desc* desc, const b200_weight_table* w,
   __nv_bfloat16* cur = e->x;          // buffer holding the residual stream (embed writes here)
   __nv_bfloat16* other = e->x_alt;
   int pending_point = -1;             // exchange point whose partials still have to be reduced into `cur`
-  int pending_grid = 0;
   int next_point = 0;
   auto make_reduce_prologue = [&](GemvPlan& pl) {  // consume the pending exchange in this plan's prologue
     pl.p.tp_world = world;
-    pl.p.tp_partials = reinterpret_cast<const float*>(e->win[e->tp_rank] + tp_slot_off(e, pending_point, 0));
-    pl.p.tp_stride = (int)(tp_vec_bytes(d.hidden) / 4);
-    pl.p.tp_wait_flag = reinterpret_cast<const unsigned long long*>(e->win[e->tp_rank] + tp_flag_off(e, pending_point));
+    pl.p.tp_partials = reinterpret_cast<const uint2*>(e->win[e->tp_rank] + tp_slot_off(e, pending_point, 0));
+    pl.p.tp_stride = (int)(tp_vec_bytes(d.hidden) / 8);
     pl.p.tp_epoch = e->tp_epoch;
-    pl.p.tp_arrivals = (unsigned int)(world * pending_grid);
     pl.p.tp_residual = cur;
     pl.p.tp_h_out = other;
     std::swap(cur, other);
@@ -462,12 +460,10 @@ static int engine_build(const b200_model_desc* desc, const b200_weight_table* w,
   };
   auto make_push_epilogue = [&](GemvPlan& pl) {
     pl.p.tp_world = world;
-    for (int r = 0; r < world; ++r) {
-      pl.p.tp_push[r] = reinterpret_cast<float*>(e->win[r] + tp_slot_off(e, next_point, e->tp_rank));
-      pl.p.tp_flag[r] = reinterpret_cast<unsigned long long*>(e->win[r] + tp_flag_off(e, next_point));
-    }
+    pl.p.tp_epoch = e->tp_epoch;
+    for (int r = 0; r < world; ++r)
+      pl.p.tp_push[r] = reinterpret_cast<uint2*>(e->win[r] + tp_slot_off(e, next_point, e->tp_rank));
     pending_point = next_point++;
-    pending_grid = pl.grid;
   };
   for (int l = 0; l < d.layers; ++l) {
     const b200_layer_weights& lw = e->lw[l];

@@ -42,13 +42,13 @@ constexpr int kMaxStages = 32;
 // per-stage barrier traffic is amortised whatever the row-block height.
 __host__ __device__ constexpr int kboxes(int rpw, int nseg) { return (4 / (rpw * nseg)) > 0 ? 4 / (rpw * nseg) : 1; }
 
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+__device__ __forceinline__ uint4 ld_volatile_u4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void red_release_sys_add(unsigned long long* p, unsigned long long v) {
-  asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void st_volatile_u2(uint2* p, const uint2 v) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
 }
 
 template <int RPW, int NSEG, int PRO, int EPI>
@@ -133,6 +133,8 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
   }
 
   pdl_wait();  // the producer kernel's output (x, residual) is complete and visible from here on
+  unsigned int tp_tag = 0;
+  if constexpr (EPI == EPI_TP_PUSH) tp_tag = (unsigned int)(*p.tp_epoch + 1ull);
   if (p.trace != nullptr && blockIdx.x == 0 && ctid == 0) p.trace[1] = global_timer_ns();
 
   if constexpr (PRO == PRO_PLAIN) {
@@ -144,23 +146,44 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
     float ss = 0.f;
     uint4 xr[kMaxHoist];
     if constexpr (PRO == PRO_TP_RMSNORM) {
-      if (ctid == 0) {
-        const unsigned long long want = (*p.tp_epoch + 1ull) * (unsigned long long)p.tp_arrivals;
-        const unsigned long long t0 = global_timer_ns();
-        while (ld_acquire_sys(p.tp_wait_flag) < want) {
-          if (global_timer_ns() - t0 > 4000000000ull) __trap();  // a peer died: fail loudly, never hang
+      // h = bf16(residual + bf16(Σ_r partial_r)) in rank order (bitwise identical on every rank).  Each partial is an
+      // 8-byte {value, tag} word written by the owning rank's GEMV epilogue; spin until the tag is this token's.
+      const unsigned int want = (unsigned int)(*p.tp_epoch + 1ull);
+      const int nq = p.k >> 2;
+      for (int i = ctid; i < nq; i += kConsumers) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < p.tp_world; ++r) {
+          const uint4* src = reinterpret_cast<const uint4*>(p.tp_partials + (size_t)r * p.tp_stride + 4 * i);
+          uint4 w0, w1;
+          unsigned int spins = 0;
+          unsigned long long t0 = 0;
+          for (;;) {
+            w0 = ld_volatile_u4(src);
+            w1 = ld_volatile_u4(src + 1);
+            if (w0.y == want && w0.w == want && w1.y == want && w1.w == want) break;
+            if ((++spins & 0x3fffu) == 0) {  // a peer died: fail loudly after ~4 s, never hang the GPU
+              const unsigned long long now = global_timer_ns();
+              if (t0 == 0) t0 = now;
+              if (now - t0 > 4000000000ull) __trap();
+            }
+          }
+          a.x += __uint_as_float(w0.x);
+          a.y += __uint_as_float(w0.z);
+          a.z += __uint_as_float(w1.x);
+          a.w += __uint_as_float(w1.z);
         }
-      }
-      named_bar_sync(1, kConsumers);
-      // h = bf16(residual + bf16(Σ partial)), staged in xs as bf16 first
-      for (int i = ctid; i < p.k; i += kConsumers) {
-        float a = 0.f;
-        for (int r = 0; r < p.tp_world; ++r) a += __ldcv(p.tp_partials + (size_t)r * p.tp_stride + i);
-        const __nv_bfloat16 h = __hadd(p.tp_residual[i], f_to_bf16(a));
-        xs[i] = h;
-        if (blockIdx.x == 0) p.tp_h_out[i] = h;
-        const float hf = bf16_to_f(h);
-        ss += hf * hf;
+        const uint2 rr = *reinterpret_cast<const uint2*>(p.tp_residual + 4 * i);
+        const __nv_bfloat162 r01 = *reinterpret_cast<const __nv_bfloat162*>(&rr.x);
+        const __nv_bfloat162 r23 = *reinterpret_cast<const __nv_bfloat162*>(&rr.y);
+        const __nv_bfloat162 h01 = __hadd2(r01, __floats2bfloat162_rn(a.x, a.y));
+        const __nv_bfloat162 h23 = __hadd2(r23, __floats2bfloat162_rn(a.z, a.w));
+        uint2 hv;
+        hv.x = *reinterpret_cast<const uint32_t*>(&h01);
+        hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+        *reinterpret_cast<uint2*>(xs + 4 * i) = hv;
+        if (blockIdx.x == 0) *reinterpret_cast<uint2*>(p.tp_h_out + 4 * i) = hv;
+        const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+        ss += f01.x * f01.x + f01.y * f01.y + f23.x * f23.x + f23.y * f23.y;
       }
     } else {
       const uint4* xg = reinterpret_cast<const uint4*>(p.x);
@@ -305,8 +328,9 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
         const float g = round_bf16(a0);
         const __nv_bfloat16 sg = f_to_bf16(g / (1.f + expf(-g)));
         p.y[row] = __hmul(sg, f_to_bf16(a1));
-      } else {  // EPI_TP_PUSH
-        for (int q = 0; q < p.tp_world; ++q) p.tp_push[q][row] = a0;
+      } else {  // EPI_TP_PUSH: one 8-byte {value, tag} store per rank, no fence needed
+        const uint2 pk = make_uint2(__float_as_uint(a0), tp_tag);
+        for (int q = 0; q < p.tp_world; ++q) st_volatile_u2(p.tp_push[q] + row, pk);
       }
     }
   }
@@ -314,11 +338,6 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
   if (p.pos_inc != nullptr && blockIdx.x == 0 && ctid == 0) *p.pos_inc += 1;
   if (p.trace != nullptr && blockIdx.x == 0 && ctid == 0) p.trace[2] = global_timer_ns();
 
-  if constexpr (EPI == EPI_TP_PUSH) {
-    __threadfence_system();
-    named_bar_sync(1, kConsumers);
-    if (ctid < p.tp_world) red_release_sys_add(p.tp_flag[ctid], 1ull);
-  }
 }
 
 // ------------------------------------------------------------------------------------------------------ dispatch

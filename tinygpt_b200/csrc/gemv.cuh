@@ -33,14 +33,13 @@ struct GemvParams {
   int stages;                     // depth of the shared-memory ring
   unsigned long long* trace;      // debug (B200_TRACE=1): CTA 0 stores globaltimer at entry / after the PDL wait / at exit
   int* pos_inc;                   // engine: when set, CTA 0 advances the token position after its last row block
-  // ---- tensor-parallel exchange (peer-mapped windows over NVLink), see tp.cuh
-  float* tp_push[kMaxTpWorld];            // EPI_TP_PUSH: slot for MY partial inside rank r's window ([n] floats)
-  unsigned long long* tp_flag[kMaxTpWorld];  // EPI_TP_PUSH: rank r's arrival counter for this exchange point
-  const float* tp_partials;               // PRO_TP_RMSNORM: local window, tp_world vectors, tp_stride floats apart
+  // ---- tensor-parallel exchange (peer-mapped windows over NVLink).  Low-latency protocol: every fp32 partial travels
+  // as ONE 8-byte store {value bits, tag} with tag = token epoch + 1, so data and "flag" arrive atomically together —
+  // no system fence, no remote atomic, no separate flag poll (the idea of NCCL's LL protocol).
+  uint2* tp_push[kMaxTpWorld];            // EPI_TP_PUSH: slot for MY partial inside rank r's window ([n] × 8 bytes)
+  const uint2* tp_partials;               // PRO_TP_RMSNORM: local window, tp_world vectors, tp_stride words apart
   int tp_stride;
-  const unsigned long long* tp_wait_flag; // PRO_TP_RMSNORM: local arrival counter
-  const unsigned long long* tp_epoch;     // device counter: tokens completed (expected arrivals = (epoch+1)*tp_arrivals)
-  unsigned int tp_arrivals;               // arrivals per token at that exchange point (world × producer CTAs)
+  const unsigned long long* tp_epoch;     // device counter: tokens completed (stable during a token)
   const __nv_bfloat16* tp_residual;       // PRO_TP_RMSNORM: hidden state before the add
   __nv_bfloat16* tp_h_out;                // PRO_TP_RMSNORM: CTA 0 stores the new hidden state (≠ tp_residual)
   int tp_world;

@@ -210,14 +210,13 @@ __global__ void __launch_bounds__(256) argmax_kernel(int64_t* __restrict__ out, 
     out[row] = idx;
     ticket[row] = 0;  // self-reset for the next launch
     if (pub.tp_world > 1 && row == 0) {
-      const int64_t gidx = idx + pub.tp_index_offset;
+      const unsigned int tag = (unsigned int)(*pub.tp_epoch + 1ull);
+      const unsigned int gidx = (unsigned int)(idx + pub.tp_index_offset);
       for (int r = 0; r < pub.tp_world; ++r) {
-        pub.tp_cand[r][0] = v;
-        *reinterpret_cast<long long*>(pub.tp_cand[r] + 2) = gidx;
+        volatile uint2* c = pub.tp_cand[r];
+        asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(c), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+        asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(c + 1), "r"(gidx), "r"(tag) : "memory");
       }
-      __threadfence_system();
-      for (int r = 0; r < pub.tp_world; ++r)
-        asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(pub.tp_flag[r]), "l"(1ull) : "memory");
     } else if (pub.cur_tok != nullptr && row == 0) {
       // engine: the greedy token becomes the next step's input and is appended to the on-device log
       *pub.cur_tok = idx;

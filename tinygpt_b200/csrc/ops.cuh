@@ -25,8 +25,8 @@ struct ArgmaxPublish {
   // rank's candidate slot and bump its arrival counter; tp_finish_kernel (engine.cu) picks the winner.
   int tp_world = 1;
   int64_t tp_index_offset = 0;
-  float* tp_cand[8] = {nullptr};
-  unsigned long long* tp_flag[8] = {nullptr};
+  uint2* tp_cand[8] = {nullptr};                 // 2 words per rank: {value bits, tag}, {global index, tag}
+  const unsigned long long* tp_epoch = nullptr;   // tag = *tp_epoch + 1
 };
 int launch_argmax(int64_t* idx, const void* logits, int64_t rows, int64_t V, void* workspace, cudaStream_t st,
                   bool pdl, const ArgmaxPublish* pub);

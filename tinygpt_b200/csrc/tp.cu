@@ -14,7 +14,7 @@ int64_t b200_tp_window_bytes(const b200_model_desc* d) {
   // candidates, +1 spare) `world` partial hidden vectors of H floats (256-byte aligned); then one 256-byte line of
   // arrival counters per point; then `world` 16-byte (max logit, global index) candidates.
   const int64_t points = 2ll * d->layers + 2;
-  const int64_t vec = ((int64_t)d->hidden * 4 + 255) / 256 * 256;
+  const int64_t vec = ((int64_t)d->hidden * 8 + 255) / 256 * 256;  // {value, tag} 8-byte words
   return points * d->tp_world * vec + points * 256 + 8 * 16 + 256;
 }
 
