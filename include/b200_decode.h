@@ -213,8 +213,8 @@ int b200_engine_decode(b200_engine* eng, int64_t n_steps, int64_t* tokens_out, v
 /* Greedy token chosen after the most recent forward/decode step (int64, device → device copy on `stream`). */
 int b200_engine_last_token(b200_engine* eng, int64_t* token_out, void* stream);
 
-/* Debug (engine created with B200_TRACE=1 in the environment): copies [launch][4] %globaltimer stamps (entry, after
- * the PDL wait, exit, unused) of the GEMV / attention launches of the most recent token into out_host; synchronises.
+/* Debug (engine created with B200_TRACE=1 in the environment): copies [launch][8] %globaltimer stamps (entry, after
+ * the PDL wait, exit, x ready, first stage landed, first row block summed, first row block stored, unused) of the GEMV / attention launches of the most recent token into out_host; synchronises.
  * Returns the number of launches copied (0 when tracing is off). */
 int64_t b200_engine_debug_trace(b200_engine* eng, uint64_t* out_host, int64_t max_entries);
 

@@ -4,7 +4,9 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "lib" / "libb200decode.so"
+import os
+
+LIB_PATH = Path(os.environ.get("B200_LIB") or (Path(__file__).resolve().parent / "lib" / "libb200decode.so"))
 IPC_HANDLE_BYTES = 64
 
 _lib = None

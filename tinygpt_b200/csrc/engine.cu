@@ -62,7 +62,7 @@ struct b200_engine {
   unsigned long long* tp_epoch = nullptr;          // tokens completed (local)
   __nv_bfloat16* x_alt = nullptr;                  // second hidden-state buffer (TP ping-pong)
   const __nv_bfloat16* x_head = nullptr;           // residual the lm_head prologue reads (TP)
-  unsigned long long* trace = nullptr;  // B200_TRACE=1: [launch][4] globaltimer stamps of the last token
+  unsigned long long* trace = nullptr;  // B200_TRACE=1: [launch][8] globaltimer stamps of the last token
   bool use_graph = true;
   bool use_pdl = true;
 };
@@ -161,7 +161,7 @@ static int engine_launch_token(b200_engine* e, cudaStream_t st, bool with_head) 
                        (int64_t)d.vocab, (int)d.hidden));
   const size_t kv_layer = (size_t)d.max_ctx * e->Hkv_l * d.head_dim;
   int slot = 0;
-  auto tr = [&]() -> unsigned long long* { return e->trace ? e->trace + 4 * (slot++) : nullptr; };
+  auto tr = [&]() -> unsigned long long* { return e->trace ? e->trace + 8 * (slot++) : nullptr; };
   for (int l = 0; l < d.layers; ++l) {
     GemvPlan q = e->p_qkv[l];
     q.p.trace = tr();
@@ -361,8 +361,8 @@ static int engine_build(const b200_model_desc* desc, const b200_weight_table* w,
   e->nsplit = attn_decode_nsplit(d.head_dim, d.max_ctx);
   env = std::getenv("B200_TRACE");
   if (env && env[0] == '1') {
-    B200_CUDA(cudaMalloc((void**)&e->trace, (size_t)(5 * d.layers + 8) * 4 * 8));
-    B200_CUDA(cudaMemset(e->trace, 0, (size_t)(5 * d.layers + 8) * 4 * 8));
+    B200_CUDA(cudaMalloc((void**)&e->trace, (size_t)(5 * d.layers + 8) * 8 * 8));
+    B200_CUDA(cudaMemset(e->trace, 0, (size_t)(5 * d.layers + 8) * 8 * 8));
   }
   e->gen_cap = 1 << 16;
 
@@ -648,7 +648,7 @@ int64_t b200_engine_position(const b200_engine* e) { return e ? e->h_pos : -1; }
 int64_t b200_engine_debug_trace(b200_engine* e, uint64_t* out_host, int64_t max_entries) {
   if (!e || !e->trace || !out_host) return 0;
   const int64_t n = std::min<int64_t>(max_entries, 5 * e->d.layers + 1);
-  if (cudaMemcpy(out_host, e->trace, (size_t)n * 4 * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  if (cudaMemcpy(out_host, e->trace, (size_t)n * 8 * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
   return n;
 }
 int64_t b200_engine_launches_per_token(const b200_engine* e) { return e ? e->launches_per_token : -1; }

@@ -20,20 +20,21 @@ eng.gen_next_token(prompt)
 eng.decode(64)
 torch.cuda.synchronize()
 n = 5 * spec.layers + 1
-buf = (C.c_uint64 * (4 * n))()
+buf = (C.c_uint64 * (8 * n))()
 got = lib().b200_engine_debug_trace(eng._h, buf, n)
 names = ["qkv", "attn", "o", "gu", "down"]
 t0 = buf[0]
 rows = []
 for i in range(got):
-    a, b, c = buf[4 * i] - t0, buf[4 * i + 1] - t0, buf[4 * i + 2] - t0
-    pro = (buf[4 * i + 3] - buf[4 * i + 1]) / 1e3 if buf[4 * i + 3] else 0.0
-    rows.append((names[i % 5] if i < 5 * spec.layers else "head", i // 5, a / 1e3, b / 1e3, c / 1e3, pro))
+    a, b, c = buf[8 * i] - t0, buf[8 * i + 1] - t0, buf[8 * i + 2] - t0
+    pro = (buf[8 * i + 3] - buf[8 * i + 1]) / 1e3 if buf[8 * i + 3] else 0.0
+    fine = tuple(((buf[8 * i + j] - buf[8 * i + 1]) / 1e3 if buf[8 * i + j] else 0.0) for j in (4, 5, 6))
+    rows.append((names[i % 5] if i < 5 * spec.layers else "head", i // 5, a / 1e3, b / 1e3, c / 1e3, pro, fine))
 print(f"{name}: kernel  layer  entry_us  after_wait_us  exit_us   (wait = after_wait-entry, body = exit-after_wait)")
 for r in rows[:12] + rows[5 * 10:5 * 10 + 6] + rows[-6:]:
     print(f"{r[0]:5s} {r[1]:3d}  {r[2]:9.2f} {r[3]:9.2f} {r[4]:9.2f}   wait {r[3]-r[2]:6.2f}  body {r[4]-r[3]:6.2f}")
 import collections
-agg = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0, 0.0])
+agg = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0])
 prev_exit = None
 for r in rows:
     a = agg[r[0]]
@@ -41,10 +42,12 @@ for r in rows:
     a[1] += r[3] - r[2]
     a[2] += r[4] - r[3]
     a[4] += r[5]
+    a[5] += r[6][0]; a[6] += r[6][1]; a[7] += r[6][2]
     if prev_exit is not None:
         a[3] += r[3] - prev_exit  # gap between the previous kernel's exit stamp and this kernel's wait return
     prev_exit = r[4]
 print("avg per kernel type: wait-before-dependency, body, gap(prev exit -> my wait return)")
-for k, (c, wt, bd, gp, pr) in agg.items():
-    print(f"  {k:5s} x{c:3d}: wait {wt/c:6.2f} us  body {bd/c:6.2f} us (prologue {pr/c:5.2f})  gap {gp/c:6.2f} us")
+for k, (c, wt, bd, gp, pr, f4, f5, f6) in agg.items():
+    print(f"  {k:5s} x{c:3d}: wait {wt/c:6.2f} us  body {bd/c:6.2f} us (x ready {pr/c:5.2f}, 1st stage {f4/c:5.2f}, "
+          f"1st block summed {f5/c:5.2f}, stored {f6/c:5.2f})  gap {gp/c:6.2f} us")
 print(f"token span {rows[-1][4]:.1f} us")

@@ -30,14 +30,14 @@ def worker(rank, world, name):
     if rank == 0:
         print(f"{name} tp{world}: {e0.elapsed_time(e1) / 32 * 1e3:.1f} us/token")
         n = 5 * spec.layers + 1
-        buf = (C.c_uint64 * (4 * n))()
+        buf = (C.c_uint64 * (8 * n))()
         got = lib().b200_engine_debug_trace(eng._h, buf, n)
         names = ["qkv", "attn", "o", "gu", "down"]
         import collections
         agg = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0, 0.0])
         prev = None
         for i in range(got):
-            a, b, c, d = (buf[4 * i + j] for j in range(4))
+            a, b, c, d = (buf[8 * i + j] for j in range(4))
             k = names[i % 5] if i < 5 * spec.layers else "head"
             g = agg[k]
             g[0] += 1; g[1] += (b - a) / 1e3; g[2] += (c - b) / 1e3
