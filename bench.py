@@ -212,15 +212,17 @@ def run_ours(args):
 
     spec = models.SPECS[args.model].with_ctx(PROMPT_LEN + NEW_TOKENS + 16)
     tp_mode = world > 1 and args.mode == "tp"
-    w_cpu = models.synth_weights(spec, seed=0)
+    # seeded synthetic checkpoint drawn on the GPU (same values on every rank: same seed, same Philox stream)
+    w_full = models.synth_weights(spec, seed=0, device=dev, device_generator=True)
     if tp_mode:
         from tinygpt_b200 import tp
-        eng = tp.TPDecodeEngine(spec, w_cpu, rank, world, dev)
+        eng = tp.TPDecodeEngine(spec, w_full, rank, world, dev)
         w = eng._w
     else:
-        w = {k: v.to(dev) for k, v in w_cpu.items()}
+        w = w_full
         eng = engine.DecodeEngine(spec, w)
-    del w_cpu
+    del w_full
+    torch.cuda.empty_cache()
     # tensor parallel: every rank decodes the SAME sequence; replicas: one independent sequence per GPU
     prompt = torch.randint(0, spec.vocab, (1, PROMPT_LEN),
                            generator=torch.Generator().manual_seed(0 if tp_mode else rank)).to(dev)

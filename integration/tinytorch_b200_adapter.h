@@ -143,24 +143,27 @@ inline void registerOps() {
 }
 
 // ------------------------------------------------------------------------------------- boundary A: whole token
-// A Module that owns a b200_engine built from the weights the reference's loader already placed on the device.
+// A Module that owns one b200_engine PER SEQUENCE of the batch, built from the weights the reference's loader already
+// placed on the device.  The engines borrow the same weights; each owns only its KV cache + workspace, so a batch of B
+// left-padded prompts (GPTEngine::generateSync, src/engine/GPTEngine.cpp:154-174) costs B caches and — for now — B
+// sequential weight passes per step (the engine is batch-1; SURVEY §8 scopes the path to batch 1).
 class B200CausalLM : public tt::nn::Module {
  public:
   // `loaded` is the reference model after ModelLoader::load (src/huggingface/ModelLoader.cpp:25-87).
   B200CausalLM(tt::nn::Module& loaded, const b200_model_desc& desc, tinygpt::KVCacheManager* refCache)
-      : desc_(desc), refCache_(refCache) {
-    std::vector<b200_layer_weights> layers(desc.layers);
-    b200_weight_table table{};
+      : desc_(desc), refCache_(refCache), layers_(desc.layers) {
     for (auto& [name, t] : loaded.namedStates()) {  // third_party/TinyTorch/src/Module/Module.h:43-53
       void* p = t->dataPtr<tt::BFloat16>();
-      auto ends = [&](const char* s) { return name.size() >= strlen(s) && name.compare(name.size() - strlen(s), strlen(s), s) == 0; };
-      if (name == "model.embed_tokens.weight") table.embed = p;
-      else if (name == "model.norm.weight") table.final_norm = p;
-      else if (name == "lm_head.weight") table.lm_head = p;
-      else if (ends("self_attn.rope.rope") && table.rope_table == nullptr) table.rope_table = t->dataPtr<float>();
+      auto ends = [&](const char* s) {
+        return name.size() >= strlen(s) && name.compare(name.size() - strlen(s), strlen(s), s) == 0;
+      };
+      if (name == "model.embed_tokens.weight") table_.embed = p;
+      else if (name == "model.norm.weight") table_.final_norm = p;
+      else if (name == "lm_head.weight") table_.lm_head = p;
+      else if (ends("self_attn.rope.rope") && table_.rope_table == nullptr) table_.rope_table = t->dataPtr<float>();
       else if (name.rfind("model.layers.", 0) == 0) {
         const int l = std::stoi(name.substr(13));
-        b200_layer_weights& w = layers[l];
+        b200_layer_weights& w = layers_[l];
         // q/k/v and gate/up are dim-0 views of ONE merged allocation (src/layer/Linear.h:64-79): the q / gate view's
         // pointer is the merged matrix.
         if (ends("input_layernorm.weight")) w.input_norm = p;
@@ -174,35 +177,47 @@ class B200CausalLM : public tt::nn::Module {
         else if (ends("mlp.down_proj.weight")) w.down_w = p;
       }
     }
-    if (table.lm_head == nullptr) table.lm_head = table.embed;  // tie_word_embeddings (GPTModel.h:39-41)
-    table.layers_host = layers.data();
-    check(b200_engine_create(&desc_, &table, &engine_), "b200_engine_create");
+    if (table_.lm_head == nullptr) table_.lm_head = table_.embed;  // tie_word_embeddings (GPTModel.h:39-41)
+    table_.layers_host = layers_.data();
   }
-  ~B200CausalLM() override { b200_engine_destroy(engine_); }
+  ~B200CausalLM() override {
+    for (b200_engine* e : engines_) b200_engine_destroy(e);
+  }
 
-  // ids [1,S] Int64 on the device → logits [1,S,V] bf16 (only the last row is computed; GPTEngine::genNextToken
-  // narrows to it, src/engine/GPTEngine.cpp:96).  A call with S > 1, or after GPTModel::resetCache(), starts a new
-  // sequence — resetCache() is non-virtual and only clears the reference's (now unused) KVCacheManager.
+  // ids [B,S] Int64 on the device → logits [B,S,V] bf16 (only the last row of each sequence is computed;
+  // GPTEngine::genNextToken narrows to it, src/engine/GPTEngine.cpp:96).  A call with S > 1, or the first call after
+  // GPTModel::resetCache() (non-virtual; it only clears the reference's now-unused KVCacheManager, which this module
+  // re-marks with a 1-row placeholder so the next reset is visible), starts new sequences.
   tt::Tensor forward(const tt::Tensor& ids) override {
-    ASSERT(ids.dim() == 2 && ids.shape(0) == 1 && ids.dtype() == tt::DType::Int64);
+    ASSERT(ids.dim() == 2 && ids.dtype() == tt::DType::Int64);
     void* stream = currentStream(ids);
-    const int64_t S = ids.shape(1);
-    if (S > 1 || (refCache_ != nullptr && refCache_->pastLength(0, 1) == 0 && b200_engine_position(engine_) > 0 && !mark_)) {
-      check(b200_engine_reset(engine_, stream), "b200_engine_reset");
+    const int64_t B = ids.shape(0), S = ids.shape(1), V = desc_.vocab;
+    while ((int64_t)engines_.size() < B) {
+      b200_engine* e = nullptr;
+      check(b200_engine_create(&desc_, &table_, &e), "b200_engine_create");
+      engines_.push_back(e);
     }
-    tt::Tensor logits = tt::Tensor::empty({1, S, (int64_t)desc_.vocab},
-                                          tt::Options(ids.device(), tt::DType::BFloat16).noGrad());
-    auto* last = logits.dataPtr<tt::BFloat16>() + (S - 1) * (int64_t)desc_.vocab;
-    check(b200_engine_forward(engine_, ids.dataPtr<int64_t>(), 1, S, last, /*logits_mode=*/0, stream),
-          "b200_engine_forward");
+    const bool fresh = S > 1 || (refCache_ != nullptr && refCache_->pastLength(0, 1) == 0);
+    tt::Tensor logits = tt::Tensor::empty({B, S, V}, tt::Options(ids.device(), tt::DType::BFloat16).noGrad());
+    for (int64_t b = 0; b < B; ++b) {
+      if (fresh) check(b200_engine_reset(engines_[b], stream), "b200_engine_reset");
+      auto* last = logits.dataPtr<tt::BFloat16>() + (b * S + (S - 1)) * V;
+      check(b200_engine_forward(engines_[b], ids.dataPtr<int64_t>() + b * S, 1, S, last, /*logits_mode=*/0, stream),
+            "b200_engine_forward");
+    }
+    if (fresh && refCache_ != nullptr) {  // leave a mark so that the next resetCache() can be told from a decode step
+      tt::Tensor mark = tt::Tensor::empty({1, 1, 1, 1}, tt::Options(ids.device(), tt::DType::BFloat16).noGrad());
+      refCache_->append(0, {mark, mark}, 1);
+    }
     return logits;
   }
 
  private:
   b200_model_desc desc_;
   tinygpt::KVCacheManager* refCache_;
-  b200_engine* engine_ = nullptr;
-  bool mark_ = false;
+  std::vector<b200_layer_weights> layers_;
+  b200_weight_table table_{};
+  std::vector<b200_engine*> engines_;
 };
 
 // GPTModel whose model() is the fused module; everything else is delegated to the loaded reference model.

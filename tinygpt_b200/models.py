@@ -92,21 +92,25 @@ SPECS: Dict[str, ModelSpec] = {s.name: s for s in
                                 TINY_MISTRAL)}
 
 
-def synth_weights(spec: ModelSpec, seed: int = 0, device: str = "cpu", std: float = 0.02) -> Dict[str, torch.Tensor]:
+def synth_weights(spec: ModelSpec, seed: int = 0, device: str = "cpu", std: float = 0.02,
+                  device_generator: bool = False) -> Dict[str, torch.Tensor]:
     """Seeded synthetic checkpoint in bf16 with the reference's state names.
 
     Matrices N(0, std); norm weights 1 + N(0, std) (so the fp32 weight multiply inside RMSNorm is exercised); qkv bias
     N(0, std).  q/k/v and gate/up are stored MERGED ("…qkv_proj.weight", "…gate_up_proj.weight": rows [q|k|v],
     [gate|up]) exactly as the reference's MergedLinear holds them; `split_views()` exposes the HF-named slices.
-    Generation is per tensor from a CPU generator so that the same seed gives the same checkpoint on every machine.
+    Generation is per tensor from a CPU generator so that the same seed gives the same checkpoint on every machine
+    (what the oracle-parity tests need).  `device_generator=True` draws on `device` instead (Philox, seconds instead of
+    minutes for 7B parameters; identical on every GPU of the same type, which is what tensor-parallel ranks need).
     """
-    g = torch.Generator(device="cpu").manual_seed(seed)
+    gen_dev = device if device_generator else "cpu"
+    g = torch.Generator(device=gen_dev).manual_seed(seed)
 
     def mat(*shape):
-        return (torch.randn(*shape, generator=g, dtype=torch.float32) * std).to(torch.bfloat16).to(device)
+        return (torch.randn(*shape, generator=g, dtype=torch.float32, device=gen_dev) * std).to(torch.bfloat16).to(device)
 
     def norm(n):
-        return (1.0 + torch.randn(n, generator=g, dtype=torch.float32) * std).to(torch.bfloat16).to(device)
+        return (1.0 + torch.randn(n, generator=g, dtype=torch.float32, device=gen_dev) * std).to(torch.bfloat16).to(device)
 
     w: Dict[str, torch.Tensor] = {}
     w["model.embed_tokens.weight"] = mat(spec.vocab, spec.hidden)

@@ -15,7 +15,7 @@ name = sys.argv[1] if len(sys.argv) > 1 else "Qwen2.5-0.5B"
 n_prof = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 pre = int(sys.argv[3]) if len(sys.argv) > 3 else 80
 spec = models.SPECS[name].with_ctx(max(256, pre + 200))
-w = {k: v.cuda() for k, v in models.synth_weights(spec, seed=0).items()}
+w = models.synth_weights(spec, seed=0, device="cuda", device_generator=True)
 eng = engine.DecodeEngine(spec, w)
 prompt = torch.randint(0, spec.vocab, (1, 16), generator=torch.Generator().manual_seed(0)).cuda()
 eng.reset_cache()

@@ -19,7 +19,7 @@ def worker(rank, world, name):
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     spec = models.SPECS[name].with_ctx(256)
-    eng = tp.TPDecodeEngine(spec, models.synth_weights(spec, seed=0), rank, world, dev)
+    eng = tp.TPDecodeEngine(spec, models.synth_weights(spec, seed=0, device=dev, device_generator=True), rank, world, dev)
     prompt = torch.randint(0, spec.vocab, (1, 16), generator=torch.Generator().manual_seed(0)).to(dev)
     eng.reset_cache()
     eng.gen_next_token(prompt)
