@@ -151,27 +151,38 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
       const unsigned int want = (unsigned int)(*p.tp_epoch + 1ull);
       const int nq = p.k >> 2;
       for (int i = ctid; i < nq; i += kConsumers) {
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int r = 0; r < p.tp_world; ++r) {
-          const uint4* src = reinterpret_cast<const uint4*>(p.tp_partials + (size_t)r * p.tp_stride + 4 * i);
-          uint4 w0, w1;
-          unsigned int spins = 0;
-          unsigned long long t0 = 0;
-          for (;;) {
-            w0 = ld_volatile_u4(src);
-            w1 = ld_volatile_u4(src + 1);
-            if (w0.y == want && w0.w == want && w1.y == want && w1.w == want) break;
-            if ((++spins & 0x3fffu) == 0) {  // a peer died: fail loudly after ~4 s, never hang the GPU
-              const unsigned long long now = global_timer_ns();
-              if (t0 == 0) t0 = now;
-              if (now - t0 > 4000000000ull) __trap();
+        // all ranks' words are requested before any is inspected (one L2 round trip, not `world` of them)
+        uint4 w0[kMaxTpWorld], w1[kMaxTpWorld];
+        unsigned int spins = 0;
+        unsigned long long t0 = 0;
+        for (;;) {
+#pragma unroll
+          for (int r = 0; r < kMaxTpWorld; ++r)
+            if (r < p.tp_world) {
+              const uint4* src = reinterpret_cast<const uint4*>(p.tp_partials + (size_t)r * p.tp_stride + 4 * i);
+              w0[r] = ld_volatile_u4(src);
+              w1[r] = ld_volatile_u4(src + 1);
             }
+          bool ok = true;
+#pragma unroll
+          for (int r = 0; r < kMaxTpWorld; ++r)
+            if (r < p.tp_world) ok = ok && w0[r].y == want && w0[r].w == want && w1[r].y == want && w1[r].w == want;
+          if (ok) break;
+          if ((++spins & 0x3fffu) == 0) {  // a peer died: fail loudly after ~4 s, never hang the GPU
+            const unsigned long long now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > 4000000000ull) __trap();
           }
-          a.x += __uint_as_float(w0.x);
-          a.y += __uint_as_float(w0.z);
-          a.z += __uint_as_float(w1.x);
-          a.w += __uint_as_float(w1.z);
         }
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < kMaxTpWorld; ++r)
+          if (r < p.tp_world) {  // rank order: bitwise identical on every rank
+            a.x += __uint_as_float(w0[r].x);
+            a.y += __uint_as_float(w0[r].z);
+            a.z += __uint_as_float(w1[r].x);
+            a.w += __uint_as_float(w1[r].z);
+          }
         const uint2 rr = *reinterpret_cast<const uint2*>(p.tp_residual + 4 * i);
         const __nv_bfloat162 r01 = *reinterpret_cast<const __nv_bfloat162*>(&rr.x);
         const __nv_bfloat162 r23 = *reinterpret_cast<const __nv_bfloat162*>(&rr.y);
