@@ -20,7 +20,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 from pathlib import Path
 
@@ -43,7 +42,7 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (one streaming `nvidia-smi -lms 100`)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -51,28 +50,32 @@ class ClockSampler:
     def __init__(self, gpu_index: int):
         self.idx = gpu_index
         self.rows = []
-        self._stop = threading.Event()
-        self._t = None
-
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.idx)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+        self._p = None
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        try:
+            self._p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                        str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                       text=True)
+            time.sleep(0.35)  # first sample before the timed region starts
+        except Exception:
+            self._p = None
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=6)
+        if self._p is None:
+            return
+        time.sleep(0.15)
+        self._p.terminate()
+        try:
+            out, _ = self._p.communicate(timeout=5)
+        except Exception:
+            self._p.kill()
+            out = ""
+        for line in (out or "").splitlines():
+            cells = [c.strip() for c in line.split(",")]
+            if len(cells) >= 9:
+                self.rows.append(cells)
 
     def summary(self):
         sm, mx, reasons = [], [], set()
