@@ -63,6 +63,12 @@ int b200_device_check(void);
 int b200_gemv_bf16(void* y, const void* x, const void* W, const void* bias_or_null, int64_t m, int64_t n, int64_t k,
                    void* stream);
 
+/* Batched (prefill) GEMM on the tcgen05 tensor cores: C[M,N] = bf16( A[M,K] · B[N,K]^T ), fp32 accumulation in TMEM,
+ * one rounding.  The m > 1 side of op::matmul for Linear layers (bias / residual are separate ops, as in the reference).
+ * [ref: TT/Operation/OpLinalg.cpp:244-277; TT/Operation/OpLinalgCuda.cuh:193-216,276-293]
+ * Requirements: K % 8 == 0, N % 8 == 0, 16-byte aligned operands. */
+int b200_gemm_bf16(void* C, const void* A, const void* B, int64_t M, int64_t N, int64_t K, void* stream);
+
 /* y[r,:] = bf16( float(x[r,:]) * rsqrtf(mean(x[r,:]^2) + eps) * float(w[:]) )  (single rounding, fp32 weight multiply)
  * [ref: TT/Operation/OpNNLayerCuda.cuh:252-357 kNormSmall/kNormLarge<RMSNorm>, host :569-619] */
 int b200_rmsnorm_bf16(void* y, const void* x, const void* w_or_null, int64_t rows, int64_t dim, float eps,

@@ -43,6 +43,7 @@ PROTOTYPES = {
     "b200_launch_count": (I64, []),
     "b200_device_check": (I32, []),
     "b200_gemv_bf16": (I32, [P, P, P, P, I64, I64, I64, P]),
+    "b200_gemm_bf16": (I32, [P, P, P, I64, I64, I64, P]),
     "b200_rmsnorm_bf16": (I32, [P, P, P, I64, I64, F, P]),
     "b200_rope_bf16": (I32, [P, P, P, I64, I64, I64, I64, I64, I32, P]),
     "b200_rope_init_f32": (I32, [P, I64, I64, F, F, F, F, I64, P]),

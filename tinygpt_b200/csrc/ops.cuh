@@ -31,6 +31,9 @@ struct ArgmaxPublish {
 int launch_argmax(int64_t* idx, const void* logits, int64_t rows, int64_t V, void* workspace, cudaStream_t st,
                   bool pdl, const ArgmaxPublish* pub);
 
+// ---- tcgen05 prefill GEMM (gemm.cu)
+int launch_gemm_bf16(void* C, const void* A, const void* B, int64_t M, int64_t N, int64_t K, cudaStream_t st);
+
 // ---- attention (attn.cu)
 // Fused decode attention of one layer for one new token (B = 1, Sq = 1):
 //   q,k,v = split(qkv)  →  optional per-head RMSNorm on q,k (Qwen3)  →  RoPE(q), RoPE(k) at position *pos  →

@@ -47,6 +47,18 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     return y
 
 
+def gemm(a: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """Batched Linear without bias on the tcgen05 tensor cores: a [..., k] · W[n, k]ᵀ → [..., n] (prefill, m > 1)."""
+    a, weight = _chk(a, "gemm.a"), _chk(weight, "gemm.weight")
+    n, k = weight.shape
+    if a.shape[-1] != k:
+        raise B200Error(f"gemm: a[..., {a.shape[-1]}] does not match W[{n}, {k}]")
+    m = a.numel() // k
+    c = torch.empty(*a.shape[:-1], n, dtype=torch.bfloat16, device=a.device)
+    check(lib().b200_gemm_bf16(c.data_ptr(), a.data_ptr(), weight.data_ptr(), m, n, k, _stream()), "b200_gemm_bf16")
+    return c
+
+
 def rms_norm(x: torch.Tensor, weight: Optional[torch.Tensor], eps: float) -> torch.Tensor:
     """function::rmsNorm(x, {dim}, w, eps)  [ref: TT/Function/FuncNNLayer.h:220-227]."""
     x = _chk(x, "rms_norm.x")
