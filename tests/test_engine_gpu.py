@@ -150,9 +150,12 @@ def test_qwen25_05b_full_size_parity(built_lib):
     check_parity(spec.name, *run_parity(spec, prompt_len=16, new_tokens=6))
 
 
-def test_full_size_properties(built_lib):
+def test_full_size_properties(built_lib, monkeypatch):
     """Size-independent checks at full size (128-token decode of config 2): determinism across runs, prefill/decode
-    consistency (forward(all tokens) reproduces the decode logits), in-range ids."""
+    consistency (forward(all tokens) reproduces the decode logits), in-range ids.  The token-by-token path is used for
+    the prompt so that re-scoring runs the very same kernels (the GEMM prefill path differs by summation order and is
+    compared separately below)."""
+    monkeypatch.setenv("B200_NO_PREFILL_GEMM", "1")
     spec = models.QWEN25_05B.with_ctx(192)
     w = {k: v.to(DEV) for k, v in models.synth_weights(spec, seed=0).items()}
     eng = engine.DecodeEngine(spec, w)
@@ -167,4 +170,57 @@ def test_full_size_properties(built_lib):
     full = torch.cat([prompt, t1[:-1].view(1, -1)], dim=1)
     logits = eng.forward(full, all_positions=True)[0, 15:]
     assert torch.equal(orc.argmax_last(logits.float().cpu()), t1.cpu()), "re-scoring the sequence reproduces the ids"
+    eng.close()
+
+
+@pytest.mark.parametrize("spec,S", [(models.TINY_QWEN2, 9), (models.TINY_QWEN3, 300), (models.TINY_LLAMA, 600),
+                                    (models.TINY_MISTRAL, 129)], ids=lambda v: getattr(v, "name", str(v)))
+def test_batched_prefill_matches_token_by_token(built_lib, spec, S, monkeypatch):
+    """The tcgen05-GEMM prefill path (S ≥ 8 tokens at once: GEMM + bias/norm/RoPE/KV-write/causal attention kernels) and
+    the decode path run token by token are the same arithmetic up to fp32 summation order: logits of the last prompt
+    position and the following greedy steps must agree like two summation orders of the oracle do, and the K/V rows
+    both paths leave in the cache must drive identical decode steps afterwards."""
+    spec = spec.with_ctx(1024)
+    w = {k: v.to(DEV) for k, v in models.synth_weights(spec, seed=4).items()}
+    prompt = torch.randint(0, spec.vocab, (1, S), generator=torch.Generator().manual_seed(S)).to(DEV)
+    monkeypatch.setenv("B200_NO_PREFILL_GEMM", "1")
+    slow = engine.DecodeEngine(spec, w)
+    monkeypatch.delenv("B200_NO_PREFILL_GEMM")
+    fast = engine.DecodeEngine(spec, w)
+    out = {}
+    for name, eng in (("token", slow), ("gemm", fast)):
+        eng.reset_cache()
+        logits = eng.forward(prompt)[0, -1].float().cpu()
+        assert eng.position == S
+        toks = eng.decode(12).cpu()
+        out[name] = (logits, toks)
+    d = (out["gemm"][0] - out["token"][0]).abs()
+    top = float(out["token"][0].abs().max())
+    ulp = 2.0 ** (torch.floor(torch.log2(torch.tensor(top))).item() - 7)
+    print(f"[{spec.name} S={S}] prefill GEMM path vs token path: mean {float(d.mean()):.3e} max {float(d.max()):.3e} "
+          f"(ulp {ulp:.3e}); decode ids equal {int((out['gemm'][1] == out['token'][1]).sum())}/12")
+    assert float(d.mean()) <= 4e-3 and float(d.max()) <= 8 * ulp
+    # and against the oracle's prefill (causal flash attention over the whole prompt)
+    cfg = to_oracle_cfg(spec)
+    wc = {k: v.float().cpu() for k, v in w.items()}
+    want = orc.forward(cfg, wc, prompt.cpu(), orc.KVCache(), models.rope_table(spec), "bf16")[0, -1]
+    d2 = (out["gemm"][0] - want).abs()
+    assert float(d2.mean()) <= 4e-3 and float(d2.max()) <= 8 * ulp, (float(d2.mean()), float(d2.max()))
+    slow.close()
+    fast.close()
+
+
+def test_prefill_then_continue_from_offset(built_lib):
+    """A second forward() of ≥ 8 tokens continues at the current position (causal mask offset by the cached prefix)."""
+    spec = models.TINY_QWEN2.with_ctx(512)
+    w = {k: v.to(DEV) for k, v in models.synth_weights(spec, seed=6).items()}
+    ids = torch.randint(0, spec.vocab, (1, 40), generator=torch.Generator().manual_seed(1)).to(DEV)
+    eng = engine.DecodeEngine(spec, w)
+    eng.reset_cache()
+    a = eng.forward(ids)[0, -1].float().cpu()           # 40 tokens in one prefill
+    eng.reset_cache()
+    eng.forward(ids[:, :17])                            # 17, then 23 more at offset 17
+    b = eng.forward(ids[:, 17:])[0, -1].float().cpu()
+    assert eng.position == 40
+    assert float((a - b).abs().max()) <= 2e-2 and float((a - b).abs().mean()) <= 2e-3
     eng.close()

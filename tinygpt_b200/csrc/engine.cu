@@ -55,6 +55,13 @@ struct b200_engine {
   int64_t h_pos = 0;
   int64_t h_gen = 0;
   int launches_per_token = 0;
+  // batched prefill (tcgen05 GEMM path), workspace allocated on first use
+  uint8_t* pf_arena = nullptr;
+  int pf_chunk = 0;  // tokens the workspace holds
+  __nv_bfloat16 *pf_x = nullptr, *pf_h = nullptr, *pf_qkv = nullptr, *pf_attn = nullptr, *pf_gu = nullptr,
+                *pf_act = nullptr, *pf_t = nullptr;
+  bool use_prefill_gemm = true;
+  const void* final_norm_w = nullptr;
   // tensor parallel
   int tp_world = 1, tp_rank = 0;
   bool shard_attn = true;
@@ -350,6 +357,9 @@ static int engine_build(const b200_model_desc* desc, const b200_weight_table* w,
   e->use_graph = !(env && env[0] == '1');
   env = std::getenv("B200_NO_PDL");
   e->use_pdl = !(env && env[0] == '1');
+  env = std::getenv("B200_NO_PREFILL_GEMM");
+  e->use_prefill_gemm = !(env && env[0] == '1');
+  e->final_norm_w = w->final_norm;
 
   int dev = 0;
   B200_CUDA(cudaGetDevice(&dev));
@@ -531,6 +541,100 @@ static int engine_build(const b200_model_desc* desc, const b200_weight_table* w,
   return B200_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ batched prefill
+// S prompt tokens at once (single GPU): activations [S, ·], every Linear on the tcgen05 GEMM, the reference's rounding
+// points kept by running bias / residual / SiLU·mul / norms as the separate ops they are in the reference
+// [ref: src/model/GPTModel.h:51-58; src/layer/Attention.h:71-112; src/layer/GatedMLP.h:37-41].  K/V rows of all S
+// tokens are written in place; the lm_head runs for the LAST position only (GPTEngine::genNextToken narrows to it).
+static constexpr int kPrefillChunk = 512;
+static constexpr int kPrefillMin = 8;
+
+static int prefill_workspace(b200_engine* e, int chunk) {
+  if (e->pf_arena != nullptr && e->pf_chunk >= chunk) return B200_OK;
+  if (e->pf_arena) {
+    B200_CUDA(cudaDeviceSynchronize());
+    cudaFree(e->pf_arena);
+    e->pf_arena = nullptr;
+  }
+  const b200_model_desc& d = e->d;
+  const size_t nqkv = (size_t)e->qdim + 2 * e->kvdim;
+  size_t off = 0;
+  auto take = [&](size_t elems) {
+    const size_t o = off;
+    off = align_up(off + elems * 2, 256);
+    return o;
+  };
+  const size_t o_x = take((size_t)chunk * d.hidden), o_h = take((size_t)chunk * d.hidden);
+  const size_t o_qkv = take((size_t)chunk * nqkv), o_attn = take((size_t)chunk * e->qdim);
+  const size_t o_gu = take((size_t)chunk * 2 * e->I_l), o_act = take((size_t)chunk * e->I_l);
+  const size_t o_t = take((size_t)chunk * d.hidden);
+  B200_CUDA(cudaMalloc((void**)&e->pf_arena, off));
+  e->pf_chunk = chunk;
+  e->pf_x = (__nv_bfloat16*)(e->pf_arena + o_x);
+  e->pf_h = (__nv_bfloat16*)(e->pf_arena + o_h);
+  e->pf_qkv = (__nv_bfloat16*)(e->pf_arena + o_qkv);
+  e->pf_attn = (__nv_bfloat16*)(e->pf_arena + o_attn);
+  e->pf_gu = (__nv_bfloat16*)(e->pf_arena + o_gu);
+  e->pf_act = (__nv_bfloat16*)(e->pf_arena + o_act);
+  e->pf_t = (__nv_bfloat16*)(e->pf_arena + o_t);
+  return B200_OK;
+}
+
+// tokens ids[0..S) at positions p0 … p0+S-1; leaves the hidden state of the last token in e->x when `last`
+static int prefill_chunk(b200_engine* e, const int64_t* ids, int S, int p0, bool last, cudaStream_t st) {
+  const b200_model_desc& d = e->d;
+  const int H = d.hidden, nqkv = e->qdim + 2 * e->kvdim;
+  const size_t kv_layer = (size_t)d.max_ctx * e->Hkv_l * d.head_dim;
+  int rc;
+  if ((rc = launch_embedding(e->pf_x, e->embed, ids, S, d.vocab, H, st, false)) != B200_OK) return rc;
+  for (int l = 0; l < d.layers; ++l) {
+    const b200_layer_weights& lw = e->lw[l];
+    if ((rc = launch_rmsnorm(e->pf_h, e->pf_x, lw.input_norm, S, H, d.rms_eps, st, false)) != B200_OK) return rc;
+    if ((rc = launch_gemm_bf16(e->pf_qkv, e->pf_h, lw.qkv_w, S, nqkv, H, st)) != B200_OK) return rc;
+    if (d.qkv_bias && (rc = launch_bias_add(e->pf_qkv, lw.qkv_b, S, nqkv, st)) != B200_OK) return rc;
+    __nv_bfloat16* kc = e->kcache + (size_t)l * kv_layer;
+    __nv_bfloat16* vc = e->vcache + (size_t)l * kv_layer;
+    if ((rc = launch_prefill_qk(e->pf_qkv, lw.q_norm, lw.k_norm, d.rms_eps, e->rope, kc, vc, S, e->Hq_l, e->Hkv_l,
+                                d.head_dim, p0, st)) != B200_OK)
+      return rc;
+    if ((rc = launch_attn_prefill(e->pf_attn, e->pf_qkv, kc, vc, S, e->Hq_l, e->Hkv_l, d.head_dim, p0, st)) != B200_OK)
+      return rc;
+    if ((rc = launch_gemm_bf16(e->pf_t, e->pf_attn, lw.o_w, S, H, e->qdim, st)) != B200_OK) return rc;
+    if ((rc = launch_add(e->pf_x, e->pf_x, e->pf_t, (int64_t)S * H, st, false)) != B200_OK) return rc;
+    if ((rc = launch_rmsnorm(e->pf_h, e->pf_x, lw.post_norm, S, H, d.rms_eps, st, false)) != B200_OK) return rc;
+    if ((rc = launch_gemm_bf16(e->pf_gu, e->pf_h, lw.gate_up_w, S, 2 * (int64_t)e->I_l, H, st)) != B200_OK) return rc;
+    if ((rc = launch_silu_mul(e->pf_act, e->pf_gu, S, e->I_l, st, false)) != B200_OK) return rc;
+    if ((rc = launch_gemm_bf16(e->pf_t, e->pf_act, lw.down_w, S, H, e->I_l, st)) != B200_OK) return rc;
+    if ((rc = launch_add(e->pf_x, e->pf_x, e->pf_t, (int64_t)S * H, st, false)) != B200_OK) return rc;
+  }
+  if (last)
+    B200_CUDA(cudaMemcpyAsync(e->x, e->pf_x + (size_t)(S - 1) * H, (size_t)H * 2, cudaMemcpyDeviceToDevice, st));
+  return B200_OK;
+}
+
+// whole prompt through the GEMM path, then lm_head + argmax for the last position
+static int engine_prefill(b200_engine* e, const int64_t* ids, int64_t S, cudaStream_t st) {
+  int rc;
+  if ((rc = prefill_workspace(e, (int)std::min<int64_t>(S, kPrefillChunk))) != B200_OK) return rc;
+  const int p_start = (int)e->h_pos;
+  for (int64_t t0 = 0; t0 < S; t0 += kPrefillChunk) {
+    const int Sc = (int)std::min<int64_t>(kPrefillChunk, S - t0);
+    if ((rc = prefill_chunk(e, ids + t0, Sc, p_start + (int)t0, t0 + Sc == S, st)) != B200_OK) return rc;
+  }
+  // the head's argmax advances pos by one: park it on the last prompt position first
+  const int v[2] = {p_start + (int)S - 1, 0};
+  B200_CUDA(cudaMemcpyAsync(e->pos, v, 4, cudaMemcpyHostToDevice, st));
+  if ((rc = gemv_launch(e->p_head, st, false)) != B200_OK) return rc;
+  int64_t* amax = reinterpret_cast<int64_t*>((uint8_t*)e->argmax_ws + argmax_workspace_bytes(1, e->V_l));
+  ArgmaxPublish pub;
+  pub.pos = e->pos;
+  pub.cur_tok = e->cur_tok;
+  pub.gen_log = e->gen_log;
+  pub.gen_count = e->gen_count;
+  pub.gen_cap = e->gen_cap;
+  return launch_argmax(amax, e->logits, 1, e->V_l, e->argmax_ws, st, false, &pub);
+}
+
 }  // namespace b200
 
 // --------------------------------------------------------------------------------------------------------- C ABI
@@ -552,6 +656,7 @@ void b200_engine_destroy(b200_engine* e) {
   if (e->g_step) cudaGraphExecDestroy(e->g_step);
   if (e->g_body) cudaGraphExecDestroy(e->g_body);
   if (e->arena) cudaFree(e->arena);
+  if (e->pf_arena) cudaFree(e->pf_arena);
   if (e->trace) cudaFree(e->trace);
   delete e;
 }
@@ -594,6 +699,15 @@ int b200_engine_forward(b200_engine* e, const int64_t* ids, int64_t B, int64_t S
   }
   cudaStream_t st = (cudaStream_t)stream;
   const size_t vbytes = (size_t)e->V_l * 2;
+  if (e->use_prefill_gemm && e->tp_world == 1 && logits_mode == 0 && S >= kPrefillMin) {
+    // batched prefill: every Linear of the prompt on the tcgen05 GEMM, lm_head for the last position only
+    int rc = engine_prefill(e, ids, S, st);
+    if (rc != B200_OK) return rc;
+    if (logits_out != nullptr) B200_CUDA(cudaMemcpyAsync(logits_out, e->logits, vbytes, cudaMemcpyDeviceToDevice, st));
+    e->h_gen += 1;
+    e->h_pos += S;
+    return B200_OK;
+  }
   for (int64_t t = 0; t < S; ++t) {
     B200_CUDA(cudaMemcpyAsync(e->cur_tok, ids + t, 8, cudaMemcpyDeviceToDevice, st));
     const bool head = (t == S - 1) || (logits_mode == 1 && logits_out != nullptr);

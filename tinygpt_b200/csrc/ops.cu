@@ -112,8 +112,8 @@ __global__ void __launch_bounds__(256) silu_mul_kernel(__nv_bfloat16* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------------------ add
-__global__ void __launch_bounds__(256) add_kernel(__nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ a,
-                                                  const __nv_bfloat16* __restrict__ b, int64_t n) {
+__global__ void __launch_bounds__(256) add_kernel(__nv_bfloat16* y, const __nv_bfloat16* a, const __nv_bfloat16* b,
+                                                  int64_t n) {  // y may alias a (prefill residual update)
   pdl_trigger();
   pdl_wait();
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x)

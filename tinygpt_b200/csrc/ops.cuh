@@ -34,6 +34,13 @@ int launch_argmax(int64_t* idx, const void* logits, int64_t rows, int64_t V, voi
 // ---- tcgen05 prefill GEMM (gemm.cu)
 int launch_gemm_bf16(void* C, const void* A, const void* B, int64_t M, int64_t N, int64_t K, cudaStream_t st);
 
+// ---- prefill helpers (prefill.cu)
+int launch_bias_add(void* y, const void* b, int64_t rows, int64_t n, cudaStream_t st);
+int launch_prefill_qk(void* qkv, const void* q_norm, const void* k_norm, float eps, const float* rope, void* kcache,
+                      void* vcache, int S, int Hq, int Hkv, int hd, int p0, cudaStream_t st);
+int launch_attn_prefill(void* o, const void* qkv, const void* kcache, const void* vcache, int S, int Hq, int Hkv, int hd,
+                        int p0, cudaStream_t st);
+
 // ---- attention (attn.cu)
 // Fused decode attention of one layer for one new token (B = 1, Sq = 1):
 //   q,k,v = split(qkv)  →  optional per-head RMSNorm on q,k (Qwen3)  →  RoPE(q), RoPE(k) at position *pos  →
