@@ -352,7 +352,10 @@ def run_ours(args):
                        ("sharded" if eng.shard_attn else "replicated (head counts do not divide)") +
                        "; hidden-vector reductions fused into the GEMV kernels over NVLink peer memory"
                        if tp_mode else f"{world} independent replicas (one sequence per GPU, no collective)"),
-                   "l2": "weights 0.99 GB > 126 MB L2: re-streamed from HBM every token, no explicit flush"},
+                   "l2": "weights 0.99 GB > 126 MB L2: re-streamed from HBM every token, no explicit flush",
+                   "kernel_sync": ("per-op completion counters (B200_FLAGSYNC=1)"
+                                   if os.environ.get("B200_FLAGSYNC") == "1" and world == 1 else
+                                   "programmatic dependent launch (griddepcontrol.wait)")},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src,
                      "kernel": f"whole decode token ({eng.launches_per_token} launches, PDL-chained; "

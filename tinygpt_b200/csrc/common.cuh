@@ -120,6 +120,51 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// ---- flag synchronisation between co-resident, PDL-launched kernels (opt-in, B200_FLAGSYNC=1; see engine.cu).
+// A kernel's CTAs count themselves "done" on a per-op counter; the dependent kernel's CTAs poll that counter instead
+// of executing griddepcontrol.wait, so they resume as soon as the LAST producer CTA has published its rows rather than
+// after the whole grid has drained and been flushed.  Counters are monotone; the target is (tokens completed + 1) ×
+// (producer CTAs), with "tokens completed" stable for the whole token (written by the last kernel of the previous one).
+struct FlagSync {
+  const unsigned long long* wait_ctr;   // producer op's completion counter, or null (= keep griddepcontrol.wait)
+  const unsigned long long* epoch;      // tokens completed by this engine
+  unsigned int wait_per_token;          // CTAs of the producer op
+  unsigned long long* signal_ctr;       // this op's completion counter
+};
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns();
+// ONE thread per CTA polls with acquire loads (each one a round trip to L2; the one that sees the target synchronises
+// with the producers' release-adds), the caller then releases the other threads through a CTA barrier.  A producer
+// that never arrives (a bug) traps after ~2 s instead of hanging the GPU.
+__device__ __forceinline__ void flag_wait(const FlagSync& fs) {
+  const unsigned long long target = (ld_relaxed_gpu_u64(fs.epoch) + 1ull) * (unsigned long long)fs.wait_per_token;
+  unsigned int spins = 0;
+  unsigned long long t0 = 0;
+  while (ld_acquire_gpu_u64(fs.wait_ctr) < target) {
+    if ((++spins & 0xfffu) == 0) {
+      const unsigned long long now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 2000000000ull) __trap();
+    }
+  }
+}
+// Called by ONE thread after a CTA barrier that follows the CTA's last global store.
+__device__ __forceinline__ void flag_signal(const FlagSync& fs) { red_release_gpu_add_u64(fs.signal_ctr, 1ull); }
+// activations written by another, still-resident kernel: read through L2 (ld.global.cg), never from a stale L1 line
+__device__ __forceinline__ uint4 ld_cg_u4(const uint4* p) { return __ldcg(p); }
+
 // ---- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -72,6 +72,11 @@ struct b200_engine {
   unsigned long long* trace = nullptr;  // B200_TRACE=1: [launch][8] globaltimer stamps of the last token
   bool use_graph = true;
   bool use_pdl = true;
+  // opt-in (B200_FLAGSYNC=1, single GPU): kernels of a token wait on per-op completion counters instead of
+  // griddepcontrol.wait (common.cuh FlagSync).  One 128-byte line per op; fs_epoch counts completed tokens.
+  bool use_flagsync = false;
+  unsigned long long* fs_ctr = nullptr;
+  unsigned long long* fs_epoch = nullptr;
 };
 
 namespace b200 {
@@ -81,7 +86,8 @@ namespace {
 // embed: x = E[cur_tok]   (first kernel of every token)
 __global__ void __launch_bounds__(128) embed_step_kernel(__nv_bfloat16* __restrict__ x,
                                                          const __nv_bfloat16* __restrict__ table,
-                                                         const int64_t* __restrict__ tok, int64_t V, int H) {
+                                                         const int64_t* __restrict__ tok, int64_t V, int H,
+                                                         unsigned long long* fs_signal) {
   pdl_trigger();
   pdl_wait();
   int64_t id = *tok;
@@ -89,6 +95,10 @@ __global__ void __launch_bounds__(128) embed_step_kernel(__nv_bfloat16* __restri
   const uint4* s4 = reinterpret_cast<const uint4*>(table + id * H);
   uint4* d4 = reinterpret_cast<uint4*>(x);
   for (int i = threadIdx.x; i < (H >> 3); i += blockDim.x) d4[i] = s4[i];
+  if (fs_signal != nullptr) {  // flag-sync engines: the first op of the token counts itself done
+    __syncthreads();
+    if (threadIdx.x == 0) red_release_gpu_add_u64(fs_signal, 1ull);
+  }
 }
 
 // Tensor parallel: last kernel of a token.  With a head: wait for every rank's (max logit, global index) candidate,
@@ -164,14 +174,33 @@ static int engine_launch_token(b200_engine* e, cudaStream_t st, bool with_head) 
   // NOTE (measured on B200, CUDA 12.9 / driver 580): when the LAST kernel node of a captured graph has a programmatic
   // (PDL) incoming edge, work enqueued after the graph launch can start before that node has finished.  The last
   // launch of each graph therefore uses a normal full dependency, and so does the first (it has no upstream).
+  // flag-sync bookkeeping: op index → counter line; every launch waits on its predecessor's line and signals its own
+  const bool fs = e->use_flagsync;
+  int fs_op = 0;
+  unsigned int fs_prev_ctas = 1;
+  auto fs_line = [&](int op) { return e->fs_ctr + (size_t)op * 16; };
+  auto fs_next = [&](unsigned int my_ctas) {  // FlagSync of the next launch in program order
+    FlagSync f{};
+    if (fs) {
+      f.wait_ctr = fs_line(fs_op);
+      f.epoch = e->fs_epoch;
+      f.wait_per_token = fs_prev_ctas;
+      f.signal_ctr = fs_line(++fs_op);
+      fs_prev_ctas = my_ctas;
+    }
+    return f;
+  };
   B200_CUDA(launch_pdl(embed_step_kernel, dim3(1), dim3(128), 0, st, false, e->x, e->embed, (const int64_t*)e->cur_tok,
-                       (int64_t)d.vocab, (int)d.hidden));
+                       (int64_t)d.vocab, (int)d.hidden, fs ? fs_line(0) : (unsigned long long*)nullptr));
+  const unsigned int attn_ctas =
+      (unsigned int)(e->nsplit * (e->Hq_l / attn_heads_per_cta(e->Hq_l, e->Hkv_l, d.max_ctx)));
   const size_t kv_layer = (size_t)d.max_ctx * e->Hkv_l * d.head_dim;
   int slot = 0;
   auto tr = [&]() -> unsigned long long* { return e->trace ? e->trace + 8 * (slot++) : nullptr; };
   for (int l = 0; l < d.layers; ++l) {
     GemvPlan q = e->p_qkv[l];
     q.p.trace = tr();
+    q.p.fs = fs_next((unsigned int)q.grid);
     if ((rc = gemv_launch(q, st, pdl)) != B200_OK) return rc;
     AttnDecodeParams a{};
     a.trace = tr();
@@ -191,22 +220,31 @@ static int engine_launch_token(b200_engine* e, cudaStream_t st, bool with_head) 
     a.Hkv = e->Hkv_l;
     a.nsplit = e->nsplit;
     a.max_ctx = d.max_ctx;
+    a.fs = fs_next(attn_ctas);
     if ((rc = launch_attn_decode(a, d.head_dim, st, pdl)) != B200_OK) return rc;
     GemvPlan o = e->p_o[l], gu = e->p_gu[l];
     o.p.trace = tr();
     gu.p.trace = tr();
+    o.p.fs = fs_next((unsigned int)o.grid);
     if ((rc = gemv_launch(o, st, pdl)) != B200_OK) return rc;
+    gu.p.fs = fs_next((unsigned int)gu.grid);
     if ((rc = gemv_launch(gu, st, pdl)) != B200_OK) return rc;
     const bool last_node = !with_head && l == d.layers - 1;
     GemvPlan dn = e->p_down[l];
     const bool tp = e->tp_world > 1;
     dn.p.pos_inc = (last_node && !tp) ? e->pos : nullptr;  // the LAST kernel of a token advances the position
     dn.p.trace = tr();
+    dn.p.fs = fs_next((unsigned int)dn.grid);
+    if (fs && last_node) {  // full dependency instead of a poll; the only place a body-only token advances the epoch
+      dn.p.fs.wait_ctr = nullptr;
+      dn.p.epoch_inc = e->fs_epoch;
+    }
     if ((rc = gemv_launch(dn, st, pdl && !(last_node && !tp))) != B200_OK) return rc;
   }
   if (with_head) {
     GemvPlan hd = e->p_head;
     hd.p.trace = tr();
+    hd.p.fs = fs_next((unsigned int)hd.grid);
     if ((rc = gemv_launch(hd, st, pdl)) != B200_OK) return rc;
     int64_t* amax = reinterpret_cast<int64_t*>((uint8_t*)e->argmax_ws + argmax_workspace_bytes(1, e->V_l));
     ArgmaxPublish pub;
@@ -216,6 +254,7 @@ static int engine_launch_token(b200_engine* e, cudaStream_t st, bool with_head) 
       pub.gen_log = e->gen_log;
       pub.gen_count = e->gen_count;
       pub.gen_cap = e->gen_cap;
+      pub.epoch_inc = fs ? e->fs_epoch : nullptr;  // full dependency on the lm_head: every CTA of the token is done
       if ((rc = launch_argmax(amax, e->logits, 1, e->V_l, e->argmax_ws, st, false, &pub)) != B200_OK) return rc;
     } else {
       pub.tp_world = e->tp_world;
@@ -357,6 +396,8 @@ static int engine_build(const b200_model_desc* desc, const b200_weight_table* w,
   e->use_graph = !(env && env[0] == '1');
   env = std::getenv("B200_NO_PDL");
   e->use_pdl = !(env && env[0] == '1');
+  env = std::getenv("B200_FLAGSYNC");
+  e->use_flagsync = (env && env[0] == '1') && world == 1 && e->use_pdl;
   env = std::getenv("B200_NO_PREFILL_GEMM");
   e->use_prefill_gemm = !(env && env[0] == '1');
   e->final_norm_w = w->final_norm;
@@ -399,6 +440,8 @@ static int engine_build(const b200_model_desc* desc, const b200_weight_table* w,
   const size_t o_pos = take(16);
   const size_t o_cnt = take(8);
   const size_t o_epoch = take(16);
+  const size_t o_fsctr = take((size_t)(5 * d.layers + 3) * 128);
+  const size_t o_fsepoch = take(16);
   e->arena_bytes = off;
   B200_CUDA(cudaMalloc((void**)&e->arena, e->arena_bytes));
   // zero only the small control region + activations (the KV cache is always written before it is read)
@@ -419,6 +462,8 @@ static int engine_build(const b200_model_desc* desc, const b200_weight_table* w,
   e->gen_log = (int64_t*)(e->arena + o_log);
   e->pos = (int*)(e->arena + o_pos);
   e->gen_count = (unsigned long long*)(e->arena + o_cnt);
+  e->fs_ctr = (unsigned long long*)(e->arena + o_fsctr);
+  e->fs_epoch = (unsigned long long*)(e->arena + o_fsepoch);
 
   // ---- shared-memory budgets.  PDL keeps two consecutive kernels resident on an SM, and a kernel's TMA ring is
   // filled while its predecessors still run; the deeper the ring, the more of a layer's weights are already on chip

@@ -51,7 +51,10 @@ __device__ __forceinline__ void st_volatile_u2(uint2* p, const uint2 v) {
   asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
 }
 
-template <int RPW, int NSEG, int PRO, int EPI>
+// FS = flag-synchronised variant (opt-in, B200_FLAGSYNC=1): the dependency on the producer kernel is a completion
+// counter polled by one thread (common.cuh FlagSync) instead of griddepcontrol.wait, activations are read through L2
+// (ld.global.cg) and the CTA counts itself done at the end.  FS = false compiles to the PDL kernel unchanged.
+template <int RPW, int NSEG, int PRO, int EPI, bool FS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap) {
   constexpr int kBoxR = kNW * RPW;
@@ -132,7 +135,21 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
     if (p.bias != nullptr && lane < RPW && my_rbs > 0 && my_row0 < p.n) bias_v = p.bias[my_row0];
   }
 
-  pdl_wait();  // the producer kernel's output (x, residual) is complete and visible from here on
+  // the producer kernel's output (x, residual) is complete and visible from here on
+  if constexpr (FS) {
+    if (p.fs.wait_ctr != nullptr) {
+      if (ctid == 0) flag_wait(p.fs);
+      named_bar_sync(1, kConsumers);
+    } else {
+      pdl_wait();  // node with a full dependency (last kernel of a graph): nothing to poll
+    }
+  } else {
+    pdl_wait();
+  }
+  auto ldx = [](const uint4* q) -> uint4 {
+    if constexpr (FS) return ld_cg_u4(q);
+    else return *q;
+  };
   unsigned int tp_tag = 0;
   if constexpr (EPI == EPI_TP_PUSH) tp_tag = (unsigned int)(*p.tp_epoch + 1ull);
   if (p.trace != nullptr && blockIdx.x == 0 && ctid == 0) p.trace[1] = global_timer_ns();
@@ -140,7 +157,7 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
   if constexpr (PRO == PRO_PLAIN) {
     const uint4* xg = reinterpret_cast<const uint4*>(p.x);
     uint4* xv = reinterpret_cast<uint4*>(xs);
-    for (int i = ctid; i < nvec_pad; i += kConsumers) xv[i] = (i < nvec) ? xg[i] : make_uint4(0, 0, 0, 0);
+    for (int i = ctid; i < nvec_pad; i += kConsumers) xv[i] = (i < nvec) ? ldx(xg + i) : make_uint4(0, 0, 0, 0);
   } else {
     // hidden vector h (k elements): either x itself, or residual + Σ_r partial_r (tensor parallel)
     float ss = 0.f;
@@ -201,7 +218,7 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
 #pragma unroll
       for (int j = 0; j < kMaxHoist; ++j) {
         const int i = ctid + j * kConsumers;
-        xr[j] = (i < nvec) ? xg[i] : make_uint4(0, 0, 0, 0);
+        xr[j] = (i < nvec) ? ldx(xg + i) : make_uint4(0, 0, 0, 0);
         float xf[8];
         unpack8(xr[j], xf);
 #pragma unroll
@@ -209,7 +226,7 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
       }
       for (int i = ctid + kMaxHoist * kConsumers; i < nvec; i += kConsumers) {
         float xf[8];
-        unpack8(xg[i], xf);
+        unpack8(ldx(xg + i), xf);
 #pragma unroll
         for (int e = 0; e < 8; ++e) ss += xf[e] * xf[e];
       }
@@ -251,7 +268,7 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
         if constexpr (PRO == PRO_TP_RMSNORM) {
           o = scale(xv[i], wg[i]);
         } else {
-          o = scale(reinterpret_cast<const uint4*>(p.x)[i], wg[i]);
+          o = scale(ldx(reinterpret_cast<const uint4*>(p.x) + i), wg[i]);
         }
       }
       xv[i] = o;
@@ -269,7 +286,10 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
     // operands of the epilogue are requested now so that their latency hides behind the k loop
     __nv_bfloat16 res_v = f_to_bf16(0.f);
     if constexpr (EPI == EPI_RESIDUAL) {
-      if (lane < RPW && row_base + lane < p.n) res_v = p.residual[row_base + lane];
+      if (lane < RPW && row_base + lane < p.n) {
+        if constexpr (FS) res_v = __ldcg(p.residual + row_base + lane);
+        else res_v = p.residual[row_base + lane];
+      }
     }
     if constexpr (EPI == EPI_PLAIN) {
       if (i > 0 && p.bias != nullptr && lane < RPW && row_base + lane < p.n) bias_v = p.bias[row_base + lane];
@@ -347,6 +367,15 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
   }
 
   if (p.pos_inc != nullptr && blockIdx.x == 0 && ctid == 0) *p.pos_inc += 1;
+  if constexpr (FS) {
+    // every consumer's rows are stored → one release-add publishes the CTA.  The token counter is advanced only by a
+    // node with a full dependency (fs.wait_ctr == null), i.e. when no CTA of the token still has to read it.
+    named_bar_sync(1, kConsumers);
+    if (ctid == 0) {
+      if (p.epoch_inc != nullptr && blockIdx.x == 0) *p.epoch_inc += 1ull;
+      if (p.fs.signal_ctr != nullptr) flag_signal(p.fs);
+    }
+  }
   if (p.trace != nullptr && blockIdx.x == 0 && ctid == 0) p.trace[2] = global_timer_ns();
 
 }
@@ -355,18 +384,25 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
 using KernelFn = void (*)(const GemvParams, const CUtensorMap);
 
 template <int RPW>
-KernelFn pick_kernel(int nseg, int pro, int epi) {
+KernelFn pick_kernel(int nseg, int pro, int epi, bool fs) {
+  if (fs) {  // the single-GPU engine's four launches per layer + lm_head
+    if (nseg == 2) return (pro == PRO_RMSNORM && epi == EPI_SILU_MUL)
+                              ? gemv_stream_kernel<RPW, 2, PRO_RMSNORM, EPI_SILU_MUL, true> : nullptr;
+    if (pro == PRO_RMSNORM && epi == EPI_PLAIN) return gemv_stream_kernel<RPW, 1, PRO_RMSNORM, EPI_PLAIN, true>;
+    if (pro == PRO_PLAIN && epi == EPI_RESIDUAL) return gemv_stream_kernel<RPW, 1, PRO_PLAIN, EPI_RESIDUAL, true>;
+    return nullptr;
+  }
   if (nseg == 2) {
     if (epi != EPI_SILU_MUL) return nullptr;
     switch (pro) {
-      case PRO_PLAIN: return gemv_stream_kernel<RPW, 2, PRO_PLAIN, EPI_SILU_MUL>;
-      case PRO_RMSNORM: return gemv_stream_kernel<RPW, 2, PRO_RMSNORM, EPI_SILU_MUL>;
-      case PRO_TP_RMSNORM: return gemv_stream_kernel<RPW, 2, PRO_TP_RMSNORM, EPI_SILU_MUL>;
+      case PRO_PLAIN: return gemv_stream_kernel<RPW, 2, PRO_PLAIN, EPI_SILU_MUL, false>;
+      case PRO_RMSNORM: return gemv_stream_kernel<RPW, 2, PRO_RMSNORM, EPI_SILU_MUL, false>;
+      case PRO_TP_RMSNORM: return gemv_stream_kernel<RPW, 2, PRO_TP_RMSNORM, EPI_SILU_MUL, false>;
     }
     return nullptr;
   }
 #define B200_PICK(P, E) \
-  if (pro == P && epi == E) return gemv_stream_kernel<RPW, 1, P, E>;
+  if (pro == P && epi == E) return gemv_stream_kernel<RPW, 1, P, E, false>;
   B200_PICK(PRO_PLAIN, EPI_PLAIN)
   B200_PICK(PRO_PLAIN, EPI_RESIDUAL)
   B200_PICK(PRO_PLAIN, EPI_TP_PUSH)
@@ -376,11 +412,11 @@ KernelFn pick_kernel(int nseg, int pro, int epi) {
   return nullptr;
 }
 
-KernelFn pick(int rpw, int nseg, int pro, int epi) {
+KernelFn pick(int rpw, int nseg, int pro, int epi, bool fs = false) {
   switch (rpw) {
-    case 1: return pick_kernel<1>(nseg, pro, epi);
-    case 2: return pick_kernel<2>(nseg, pro, epi);
-    case 4: return pick_kernel<4>(nseg, pro, epi);
+    case 1: return pick_kernel<1>(nseg, pro, epi, fs);
+    case 2: return pick_kernel<2>(nseg, pro, epi, fs);
+    case 4: return pick_kernel<4>(nseg, pro, epi, fs);
   }
   return nullptr;
 }
@@ -395,8 +431,9 @@ int gemv_setup_attributes() {
     for (int rpw : rpws)
       for (int nseg = 1; nseg <= 2; ++nseg)
         for (int pro = 0; pro < 3; ++pro)
-          for (int epi = 0; epi < 4; ++epi) {
-            KernelFn f = pick(rpw, nseg, pro, epi);
+          for (int epi = 0; epi < 4; ++epi)
+            for (int fs = 0; fs < 2; ++fs) {
+            KernelFn f = pick(rpw, nseg, pro, epi, fs != 0);
             if (!f) continue;
             cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemvMaxSmem + 4096);
             // one carveout for every kernel of the token: a change of carveout between launches drains the SM and
@@ -498,9 +535,10 @@ int gemv_make_plan(GemvPlan* plan, const void* W, int64_t rows_total, int64_t n,
 }
 
 int gemv_launch(const GemvPlan& plan, cudaStream_t stream, bool pdl) {
-  KernelFn f = pick(plan.rpw, plan.nseg, plan.pro, plan.epi);
+  const bool fs = plan.p.fs.signal_ctr != nullptr || plan.p.fs.wait_ctr != nullptr;
+  KernelFn f = pick(plan.rpw, plan.nseg, plan.pro, plan.epi, fs);
   if (!f) {
-    set_error("gemv: no kernel instantiation");
+    set_error("gemv: no kernel instantiation (nseg=%d pro=%d epi=%d flag-sync=%d)", plan.nseg, plan.pro, plan.epi, (int)fs);
     return B200_ERR_INVALID;
   }
   B200_CUDA(launch_pdl(f, dim3(plan.grid), dim3(kThreads), (size_t)plan.smem, stream, pdl, plan.p, plan.tmap));

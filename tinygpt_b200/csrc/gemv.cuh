@@ -33,6 +33,8 @@ struct GemvParams {
   int stages;                     // depth of the shared-memory ring
   unsigned long long* trace;      // debug (B200_TRACE=1): CTA 0 stores globaltimer at entry / after the PDL wait / at exit
   int* pos_inc;                   // engine: when set, CTA 0 advances the token position after its last row block
+  unsigned long long* epoch_inc;  // flag-sync engines: … and the count of completed tokens (with pos_inc)
+  FlagSync fs;                    // opt-in flag synchronisation (common.cuh); fs.signal_ctr == null ⇒ plain PDL kernel
   // ---- tensor-parallel exchange (peer-mapped windows over NVLink).  Low-latency protocol: every fp32 partial travels
   // as ONE 8-byte store {value bits, tag} with tag = token epoch + 1, so data and "flag" arrive atomically together —
   // no system fence, no remote atomic, no separate flag poll (the idea of NCCL's LL protocol).

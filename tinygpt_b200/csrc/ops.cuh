@@ -23,6 +23,7 @@ struct ArgmaxPublish {
   int gen_cap = 1;
   // tensor parallel (vocabulary-sharded lm_head): instead of publishing, push (max logit, GLOBAL index) into every
   // rank's candidate slot and bump its arrival counter; tp_finish_kernel (engine.cu) picks the winner.
+  unsigned long long* epoch_inc = nullptr;  // flag-sync engines: count of completed tokens, advanced with pos
   int tp_world = 1;
   int64_t tp_index_offset = 0;
   uint2* tp_cand[8] = {nullptr};                 // 2 words per rank: {value bits, tag}, {global index, tag}
@@ -61,6 +62,7 @@ struct AttnDecodeParams {
   unsigned int* tickets;         // [Hq], zero-initialised, self-resetting
   int heads_per_cta;             // 0 = choose from max_ctx (attn_heads_per_cta)
   unsigned long long* trace;     // debug timestamps (see GemvParams::trace)
+  FlagSync fs;                   // opt-in flag synchronisation (common.cuh); signal_ctr == null ⇒ plain PDL kernel
   int Hq, Hkv, nsplit, max_ctx;  // nsplit = attn_decode_nsplit(hd, max_ctx): fixed 256 (hd 64) / 128 (hd 128) keys per split
 };
 int attn_decode_nsplit(int hd, int max_ctx);
