@@ -73,3 +73,61 @@ def test_flagsync_full_size_repeatable(built_lib, monkeypatch):
         eng.close()
         del w
     assert torch.equal(runs[0], runs[1]) and torch.equal(runs[1], runs[2])
+
+
+# ------------------------------------------------------------------------------ tensor-core prefill attention (mma.sync)
+def _urand(*shape, seed):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand(*shape, generator=g) * 2 - 1).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("B,S,Hq,Hkv,hd", [(2, 64, 4, 4, 128), (2, 67, 4, 2, 64), (1, 128, 14, 2, 64), (1, 1, 2, 1, 64),
+                                            (3, 200, 8, 8, 128), (1, 513, 16, 8, 128), (1, 2, 1, 1, 128)])
+def test_mma_causal_attention_vs_oracle(built_lib, B, S, Hq, Hkv, hd, monkeypatch):
+    from tinygpt_b200 import ops
+    q, k, v = _urand(B, S, Hq, hd, seed=42), _urand(B, S, Hkv, hd, seed=43), _urand(B, S, Hkv, hd, seed=44)
+    monkeypatch.setenv("B200_PREFILL_ATTN", "mma")
+    got = ops.flash_attention(q.to(DEV), k.to(DEV), v.to(DEV), True).float().cpu()
+    monkeypatch.delenv("B200_PREFILL_ATTN")
+    base = ops.flash_attention(q.to(DEV), k.to(DEV), v.to(DEV), True).float().cpu()   # verified CUDA-core kernel
+    naive = orc.naive_attention(q, k, v, True)
+    err = (got - naive).abs()
+    assert bool((err <= 1e-2 + 1e-1 * naive.abs()).all()), f"TinyFA bf16 tolerance violated: max {float(err.max())}"
+    want = orc.flash_attention(q, k, v, True)
+    assert_close_bf16(got, want, 4, "mma prefill attention vs oracle tile walk", atol=4e-3)
+    assert_close_bf16(got, base, 6, "mma prefill attention vs the CUDA-core kernel", atol=6e-3)
+
+
+@pytest.mark.parametrize("spec,S", [(models.TINY_QWEN2, 9), (models.TINY_QWEN3, 300), (models.TINY_LLAMA, 600),
+                                    (models.TINY_MISTRAL, 129)], ids=lambda v: getattr(v, "name", str(v)))
+def test_mma_prefill_through_engine(built_lib, spec, S, monkeypatch):
+    """Whole batched prefill with the tensor-core attention vs the oracle's causal prefill, then a second chunk at an
+    offset (mask shifted by the cached prefix) vs one-shot."""
+    spec = spec.with_ctx(1024)
+    w = {k: v.to(DEV) for k, v in models.synth_weights(spec, seed=4).items()}
+    prompt = torch.randint(0, spec.vocab, (1, S), generator=torch.Generator().manual_seed(S)).to(DEV)
+    monkeypatch.setenv("B200_PREFILL_ATTN", "mma")
+    eng = engine.DecodeEngine(spec, w)
+    eng.reset_cache()
+    got = eng.forward(prompt)[0, -1].float().cpu()
+    toks = eng.decode(8).cpu()
+    eng.reset_cache()
+    cut = max(8, S // 3)
+    if S - cut >= 8:
+        eng.forward(prompt[:, :cut])
+        two = eng.forward(prompt[:, cut:])[0, -1].float().cpu()
+        assert float((two - got).abs().max()) <= 2e-2 and float((two - got).abs().mean()) <= 2e-3
+    monkeypatch.delenv("B200_PREFILL_ATTN")
+    eng.reset_cache()
+    base = eng.forward(prompt)[0, -1].float().cpu()
+    base_toks = eng.decode(8).cpu()
+    cfg = to_oracle_cfg(spec)
+    wc = {k: v.float().cpu() for k, v in w.items()}
+    want = orc.forward(cfg, wc, prompt.cpu(), orc.KVCache(), models.rope_table(spec), "bf16")[0, -1]
+    top = float(want.abs().max())
+    ulp = 2.0 ** (torch.floor(torch.log2(torch.tensor(top))).item() - 7)
+    d = (got - want).abs()
+    print(f"[{spec.name} S={S}] mma prefill vs oracle: mean {float(d.mean()):.3e} max {float(d.max()):.3e}; "
+          f"vs CUDA-core prefill max {float((got - base).abs().max()):.3e}; ids equal {int((toks == base_toks).sum())}/8")
+    assert float(d.mean()) <= 4e-3 and float(d.max()) <= 8 * ulp
+    eng.close()

@@ -499,5 +499,7 @@ extern "C" int b200_attn_bf16(void* o, const void* q, const void* k, const void*
                               int64_t Hq, int64_t Hkv, int64_t hd, int causal, void* stream) {
   using namespace b200;
   B200_CHECK_ARG(o && q && k && v, "attention: null pointer");
+  if (causal && Sq == Skv && Sq > 1 && prefill_attn_mma_enabled())
+    return launch_attn_causal_mma(o, q, k, v, B, Sq, Hq, Hkv, hd, (cudaStream_t)stream);
   return launch_attn_general(o, q, k, v, B, Sq, Skv, Hq, Hkv, hd, causal, (cudaStream_t)stream);
 }

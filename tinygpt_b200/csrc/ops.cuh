@@ -42,6 +42,13 @@ int launch_prefill_qk(void* qkv, const void* q_norm, const void* k_norm, float e
 int launch_attn_prefill(void* o, const void* qkv, const void* kcache, const void* vcache, int S, int Hq, int Hkv, int hd,
                         int p0, cudaStream_t st);
 
+// ---- tensor-core prefill attention (prefill_attn.cu), opt-in: B200_PREFILL_ATTN=mma
+bool prefill_attn_mma_enabled();
+int launch_attn_prefill_mma(void* o, const void* qkv, const void* kcache, const void* vcache, int S, int Hq, int Hkv, int hd,
+                            int p0, cudaStream_t st);
+int launch_attn_causal_mma(void* o, const void* q, const void* k, const void* v, int64_t B, int64_t S, int64_t Hq,
+                           int64_t Hkv, int64_t hd, cudaStream_t st);
+
 // ---- attention (attn.cu)
 // Fused decode attention of one layer for one new token (B = 1, Sq = 1):
 //   q,k,v = split(qkv)  →  optional per-head RMSNorm on q,k (Qwen3)  →  RoPE(q), RoPE(k) at position *pos  →

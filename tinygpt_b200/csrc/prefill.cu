@@ -179,6 +179,7 @@ int launch_prefill_qk(void* qkv, const void* q_norm, const void* k_norm, float e
 int launch_attn_prefill(void* o, const void* qkv, const void* kcache, const void* vcache, int S, int Hq, int Hkv, int hd,
                         int p0, cudaStream_t st) {
   B200_CHECK_ARG(hd == 64 || hd == 128, "prefill: head_dim %d not built", hd);
+  if (prefill_attn_mma_enabled()) return launch_attn_prefill_mma(o, qkv, kcache, vcache, S, Hq, Hkv, hd, p0, st);
   dim3 grid((unsigned)S, (unsigned)Hq);
   g_launches.fetch_add(1);
   if (hd == 64)
