@@ -219,6 +219,19 @@ int b200_engine_decode(b200_engine* eng, int64_t n_steps, int64_t* tokens_out, v
 /* Greedy token chosen after the most recent forward/decode step (int64, device → device copy on `stream`). */
 int b200_engine_last_token(b200_engine* eng, int64_t* token_out, void* stream);
 
+/* Async token pipeline [ref: src/engine/GPTEngine.cpp:17-35 AsyncTokenPipeline / DefaultTokenPipeline::fetchTokenId —
+ * a blocking Tensor::item() per token — and :180-232 generateAsync].  Here the kernel that picks the greedy token also
+ * posts it into a ring in PINNED, device-mapped HOST memory, as ONE 8-byte word
+ *     ((n & 0xffffffff) << 32) | (uint32)token        n = 1-based count of tokens this engine has generated
+ * at ring[(n - 1) % capacity], so the host reads tokens by polling memory: no stream synchronisation, no memcpy, and
+ * the engine can run several steps ahead of the consumer (EOS / abort: stop launching, b200_engine_seek back).
+ * `ring_host_mapped` must be 8-byte aligned pinned memory that the device can address (cudaHostAlloc /
+ * cudaHostRegister; with unified addressing the host pointer itself), zero-initialised, alive until the mailbox is
+ * cleared with ring = NULL or the engine destroyed.  Re-captures the per-token graphs; single-GPU engines only. */
+int b200_engine_set_mailbox(b200_engine* eng, uint64_t* ring_host_mapped, int64_t capacity, void* stream);
+/* Host-side mirror: how many tokens this engine has generated (= n of the most recently enqueued token). */
+int64_t b200_engine_generated(const b200_engine* eng);
+
 /* Debug (engine created with B200_TRACE=1 in the environment): copies [launch][8] %globaltimer stamps (entry, after
  * the PDL wait, exit, x ready, first stage landed, first row block summed, first row block stored, unused) of the GEMV / attention launches of the most recent token into out_host; synchronises.
  * Returns the number of launches copied (0 when tracing is off). */

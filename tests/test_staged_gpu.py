@@ -131,3 +131,35 @@ def test_mma_prefill_through_engine(built_lib, spec, S, monkeypatch):
           f"vs CUDA-core prefill max {float((got - base).abs().max()):.3e}; ids equal {int((toks == base_toks).sum())}/8")
     assert float(d.mean()) <= 4e-3 and float(d.max()) <= 8 * ulp
     eng.close()
+
+
+# ------------------------------------------------------------------------------------ async token pipeline (mailbox)
+def test_generate_async_matches_sync_and_stops(built_lib):
+    """generate_async hands out exactly generate_sync's tokens through the pinned-host mailbox (ring smaller than the
+    sequence → wrap-around), stops at an EOS id / on callback abort, and leaves the engine positioned for continuation."""
+    spec = models.TINY_QWEN2.with_ctx(256)
+    w = {k: v.to(DEV) for k, v in models.synth_weights(spec, seed=2).items()}
+    eng = engine.DecodeEngine(spec, w)
+    prompt = torch.randint(0, spec.vocab, (11,), generator=torch.Generator().manual_seed(3)).tolist()
+    want = eng.generate_sync(prompt, 40).tolist()
+    eng.set_mailbox(8)
+    seen = []
+    got, reason = eng.generate_async(prompt, 40, callback=lambda t: seen.append(t) or True, lookahead=3)
+    assert got == want and seen == want and reason == "length"
+    # EOS: the 7th token is declared EOS → 6 tokens come out; the steps that ran ahead are rewound
+    eos = want[6]
+    first_eos = want.index(eos)
+    got, reason = eng.generate_async(prompt, 40, eos_ids=[eos], lookahead=4)
+    assert got == want[:first_eos] and reason == "stop"
+    assert eng.position == len(prompt) + max(first_eos, 1) - 1
+    # continuing from there with the last kept token reproduces the sync sequence
+    if first_eos >= 1:
+        nxt = eng.gen_next_token(torch.tensor([[want[first_eos - 1]]], device=DEV))
+        assert int(nxt) == want[first_eos]
+    # abort from the callback after 5 tokens
+    got, reason = eng.generate_async(prompt, 40, callback=lambda t: len(got_so_far.append(t) or got_so_far) < 5,
+                                     lookahead=2) if (got_so_far := []) is not None else (None, None)
+    assert got == want[:5] and reason == "stop"
+    eng.clear_mailbox()
+    assert eng.generate_sync(prompt, 12).tolist() == want[:12]
+    eng.close()

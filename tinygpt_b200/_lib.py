@@ -65,6 +65,8 @@ PROTOTYPES = {
     "b200_engine_last_token": (I32, [P, P, P]),
     "b200_engine_debug_trace": (I64, [P, P, I64]),
     "b200_engine_position": (I64, [P]),
+    "b200_engine_generated": (I64, [P]),
+    "b200_engine_set_mailbox": (I32, [P, P, I64, P]),
     "b200_engine_launches_per_token": (I64, [P]),
     "b200_engine_bytes_per_token": (I64, [P, I64]),
     "b200_tp_window_bytes": (I64, [C.POINTER(ModelDesc)]),

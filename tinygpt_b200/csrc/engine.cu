@@ -74,6 +74,9 @@ struct b200_engine {
   bool use_pdl = true;
   // opt-in (B200_FLAGSYNC=1, single GPU): kernels of a token wait on per-op completion counters instead of
   // griddepcontrol.wait (common.cuh FlagSync).  One 128-byte line per op; fs_epoch counts completed tokens.
+  // async token pipeline (b200_engine_set_mailbox): ring in pinned host memory the argmax kernel posts tokens into
+  unsigned long long* mailbox = nullptr;
+  unsigned long long mailbox_cap = 1;
   bool use_flagsync = false;
   unsigned long long* fs_ctr = nullptr;
   unsigned long long* fs_epoch = nullptr;
@@ -255,6 +258,8 @@ static int engine_launch_token(b200_engine* e, cudaStream_t st, bool with_head) 
       pub.gen_count = e->gen_count;
       pub.gen_cap = e->gen_cap;
       pub.epoch_inc = fs ? e->fs_epoch : nullptr;  // full dependency on the lm_head: every CTA of the token is done
+      pub.mailbox = e->mailbox;
+      pub.mailbox_cap = e->mailbox_cap;
       if ((rc = launch_argmax(amax, e->logits, 1, e->V_l, e->argmax_ws, st, false, &pub)) != B200_OK) return rc;
     } else {
       pub.tp_world = e->tp_world;
@@ -677,6 +682,8 @@ static int engine_prefill(b200_engine* e, const int64_t* ids, int64_t S, cudaStr
   pub.gen_log = e->gen_log;
   pub.gen_count = e->gen_count;
   pub.gen_cap = e->gen_cap;
+  pub.mailbox = e->mailbox;
+  pub.mailbox_cap = e->mailbox_cap;
   return launch_argmax(amax, e->logits, 1, e->V_l, e->argmax_ws, st, false, &pub);
 }
 
@@ -803,6 +810,40 @@ int b200_engine_last_token(b200_engine* e, int64_t* token_out, void* stream) {
 }
 
 int64_t b200_engine_position(const b200_engine* e) { return e ? e->h_pos : -1; }
+int64_t b200_engine_generated(const b200_engine* e) { return e ? e->h_gen : -1; }
+
+int b200_engine_set_mailbox(b200_engine* e, uint64_t* ring, int64_t capacity, void* stream) {
+  using namespace b200;
+  B200_CHECK_ARG(e, "engine_set_mailbox: null engine");
+  B200_CHECK_ARG(ring == nullptr || (capacity >= 2 && (reinterpret_cast<uintptr_t>(ring) & 7) == 0),
+                 "engine_set_mailbox: ring must be 8-byte aligned with capacity >= 2");
+  if (e->tp_world > 1) {
+    set_error("engine_set_mailbox: tensor-parallel engines publish through tp_finish_kernel; mailbox not built");
+    return B200_ERR_UNSUPPORTED;
+  }
+  if (ring != nullptr) {  // the pointer must be addressable from the device
+    cudaPointerAttributes at{};
+    cudaError_t err = cudaPointerGetAttributes(&at, ring);
+    if (err != cudaSuccess || at.type != cudaMemoryTypeHost || at.devicePointer == nullptr) {
+      (void)cudaGetLastError();
+      set_error("engine_set_mailbox: ring is not pinned, device-mapped host memory");
+      return B200_ERR_INVALID;
+    }
+    ring = static_cast<uint64_t*>(at.devicePointer);
+  }
+  // graphs in flight keep the old parameters: drain the stream, then re-capture with the new ring baked in
+  B200_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  e->mailbox = reinterpret_cast<unsigned long long*>(ring);
+  e->mailbox_cap = ring ? (unsigned long long)capacity : 1ull;
+  if (e->use_graph) {
+    cudaGraphExec_t fresh = nullptr;
+    int rc = engine_capture(e, true, &fresh);
+    if (rc != B200_OK) return rc;
+    if (e->g_step) cudaGraphExecDestroy(e->g_step);
+    e->g_step = fresh;
+  }
+  return B200_OK;
+}
 
 int64_t b200_engine_debug_trace(b200_engine* e, uint64_t* out_host, int64_t max_entries) {
   if (!e || !e->trace || !out_host) return 0;

@@ -225,6 +225,11 @@ __global__ void __launch_bounds__(256) argmax_kernel(int64_t* __restrict__ out, 
       const unsigned long long c = *pub.gen_count;
       pub.gen_log[c % (unsigned long long)pub.gen_cap] = idx;
       *pub.gen_count = c + 1;
+      if (pub.mailbox != nullptr) {  // one posted 8-byte write to host memory: {sequence tag, token} arrive together
+        const unsigned long long word = (((c + 1ull) & 0xffffffffull) << 32) | (unsigned long long)(unsigned int)idx;
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(pub.mailbox + (c % pub.mailbox_cap)), "l"(word)
+                     : "memory");
+      }
     }
   }
 }

@@ -24,6 +24,9 @@ struct ArgmaxPublish {
   // tensor parallel (vocabulary-sharded lm_head): instead of publishing, push (max logit, GLOBAL index) into every
   // rank's candidate slot and bump its arrival counter; tp_finish_kernel (engine.cu) picks the winner.
   unsigned long long* epoch_inc = nullptr;  // flag-sync engines: count of completed tokens, advanced with pos
+  // async token pipeline: ring in pinned, device-mapped host memory (b200_engine_set_mailbox); null = none
+  unsigned long long* mailbox = nullptr;
+  unsigned long long mailbox_cap = 1;
   int tp_world = 1;
   int64_t tp_index_offset = 0;
   uint2* tp_cand[8] = {nullptr};                 // 2 words per rank: {value bits, tag}, {global index, tag}

@@ -4,13 +4,15 @@
   DecodeEngine.reset_cache()     ↔ GPTModel::resetCache                             [ref: src/model/GPTModel.h:91-94]
   DecodeEngine.gen_next_token()  ↔ GPTEngine::genNextToken (greedy sampler)         [ref: src/engine/GPTEngine.cpp:94-99]
   DecodeEngine.generate_sync()   ↔ GPTEngine::generateSync, batch 1, greedy         [ref: src/engine/GPTEngine.cpp:154-174]
+  DecodeEngine.generate_async()  ↔ GPTEngine::generateAsync + AsyncTokenPipeline    [ref: src/engine/GPTEngine.cpp:17-35,180-232]
 
 torch is used for device memory, pinned host buffers and the current stream only.
 """
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, List, Optional
+import time
+from typing import Callable, Dict, Iterable, List, Optional, Tuple
 
 import torch
 
@@ -158,3 +160,76 @@ class DecodeEngine:
         pinned_out[:max_new_tokens].copy_(toks, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return pinned_out[:max_new_tokens].clone()
+
+    # ----------------------------------------------------------------------------------------- generateAsync
+    def set_mailbox(self, capacity: int = 64) -> torch.Tensor:
+        """Attach a token mailbox: a zeroed ring of `capacity` 8-byte words in pinned host memory that the argmax kernel
+        posts {sequence tag, token} into (b200_engine_set_mailbox).  Returns the ring (int64 view of the words)."""
+        ring = torch.zeros(capacity, dtype=torch.int64).pin_memory()
+        check(lib().b200_engine_set_mailbox(self._h, ring.data_ptr(), capacity, self._stream()),
+              "b200_engine_set_mailbox")
+        self._ring, self._ring_np = ring, ring.numpy()  # numpy view: every element read is a fresh load
+        return ring
+
+    def clear_mailbox(self) -> None:
+        check(lib().b200_engine_set_mailbox(self._h, None, 0, self._stream()), "b200_engine_set_mailbox")
+        self._ring = self._ring_np = None
+
+    def _fetch_token(self, n: int, timeout_s: float = 30.0) -> int:
+        """Token number n (1-based count of tokens this engine generated) from the mailbox; spins on host memory."""
+        cap = self._ring_np.shape[0]
+        tag = n & 0xFFFFFFFF
+        t0 = None
+        while True:
+            word = int(self._ring_np[(n - 1) % cap]) & 0xFFFFFFFFFFFFFFFF
+            if (word >> 32) == tag:
+                return word & 0xFFFFFFFF
+            if t0 is None:
+                t0 = time.perf_counter()
+            elif time.perf_counter() - t0 > timeout_s:
+                raise B200Error(f"generate_async: token {n} did not arrive within {timeout_s} s")
+
+    def generate_async(self, prompt_ids, max_new_tokens: int, callback: Optional[Callable[[int], bool]] = None,
+                       eos_ids: Iterable[int] = (), lookahead: int = 4) -> Tuple[List[int], str]:
+        """GPTEngine::generateAsync for one sequence, greedy: tokens are handed to `callback(token_id) -> keep_going`
+        as they are produced while the engine already runs up to `lookahead` steps ahead; no stream synchronisation or
+        memcpy per token (the reference blocks on Tensor::item() for each one).  Stops at an EOS id (not passed to the
+        callback, like the reference), when the callback returns False, or after max_new_tokens.
+        Returns (token ids handed out, finish reason 'stop' | 'length').  Afterwards the engine is positioned so that
+        feeding the next input token continues the sequence (steps that ran ahead of the stop are rewound)."""
+        if max_new_tokens < 1:
+            raise B200Error("generate_async: max_new_tokens must be >= 1")
+        if getattr(self, "_ring_np", None) is None:
+            self.set_mailbox(max(64, 4 * lookahead))
+        if lookahead < 1 or lookahead >= self._ring_np.shape[0]:
+            raise B200Error("generate_async: lookahead must be in [1, mailbox capacity)")
+        eos = set(int(t) for t in eos_ids)
+        prompt = torch.as_tensor(prompt_ids, dtype=torch.int64).view(1, -1)
+        if prompt.numel() == 0:
+            raise B200Error("generate_async: empty prompt")
+        S = prompt.shape[1]
+        ids_dev = prompt.pin_memory().to(self.device, non_blocking=True)
+        self.reset_cache()
+        base = int(lib().b200_engine_generated(self._h))      # tokens generated before this call
+        stream = self._stream()
+        check(lib().b200_engine_forward(self._h, ids_dev.data_ptr(), 1, S, None, 0, stream), "b200_engine_forward")
+        launched, out, reason = 1, [], "length"
+        while len(out) < max_new_tokens:
+            while launched < max_new_tokens and launched - len(out) < lookahead:
+                check(lib().b200_engine_decode(self._h, 1, None, stream), "b200_engine_decode")
+                launched += 1
+            tok = self._fetch_token(base + len(out) + 1)
+            if tok in eos:
+                reason = "stop"
+                break
+            out.append(tok)
+            if callback is not None and not callback(tok):
+                reason = "stop"
+                break
+        torch.cuda.current_stream(self.device).synchronize()
+        # position of the next input token = S + (tokens kept) - 1 … the last kept token has not been fed yet unless a
+        # look-ahead step consumed it; rewinding there makes both cases equal
+        keep = max(len(out), 1)
+        if S + keep - 1 < self.position:
+            self.seek(S + keep - 1)
+        return out, reason
