@@ -163,3 +163,48 @@ def test_generate_async_matches_sync_and_stops(built_lib):
     eng.clear_mailbox()
     assert eng.generate_sync(prompt, 12).tolist() == want[:12]
     eng.close()
+
+
+# ---------------------------------------------------------------------- persistent 128×256 tcgen05 GEMM (B200_GEMM=persistent)
+def _rand_bf16(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 128, 256), (256, 384, 512), (16, 1152, 896), (200, 896, 4864),
+                                   (1, 128, 64), (130, 136, 72), (2048, 4096, 2048), (512, 12288, 2048),
+                                   (2048, 2048, 6144), (384, 40000, 128)])
+def test_persistent_gemm_vs_oracle_and_v1(built_lib, M, N, K, monkeypatch):
+    """Same gate as tests/test_gemm_gpu.py, and equality with the verified one-tile-per-CTA kernel: both accumulate the
+    same bf16 products in fp32 on the same tensor cores in the same k order, so they should agree bit for bit."""
+    from tinygpt_b200 import ops
+    a, w = _rand_bf16(M, K, seed=M + K), _rand_bf16(N, K, seed=N, scale=0.02)
+    monkeypatch.setenv("B200_GEMM", "persistent")
+    got = ops.gemm(a.to(DEV), w.to(DEV))
+    got2 = ops.gemm(a.to(DEV), w.to(DEV))            # TMEM buffers / barriers re-used correctly on a second launch
+    monkeypatch.delenv("B200_GEMM")
+    base = ops.gemm(a.to(DEV), w.to(DEV))
+    assert torch.equal(got, got2)
+    if M * N * K <= 2 ** 31:
+        want = orc.linear(a, w, None)
+    else:
+        want = (a.to(DEV).float() @ w.to(DEV).float().t()).to(torch.bfloat16).float().cpu()
+    assert_close_bf16(got, want, 1, f"persistent gemm {M}x{N}x{K}", atol=1e-4, frac_exact=0.97)
+    same = float((got == base).float().mean())
+    print(f"[persistent gemm {M}x{N}x{K}] bit-identical to the 128x128 kernel on {same:.5f} of the elements")
+    assert same >= 0.999
+
+
+def test_prefill_chunk_override(built_lib, monkeypatch):
+    """B200_PREFILL_CHUNK=2048: one pass instead of chunks of 512 — same logits up to summation order."""
+    spec = models.TINY_LLAMA.with_ctx(2304)
+    w = {k: v.to(DEV) for k, v in models.synth_weights(spec, seed=4).items()}
+    prompt = torch.randint(0, spec.vocab, (1, 1500), generator=torch.Generator().manual_seed(5)).to(DEV)
+    eng = engine.DecodeEngine(spec, w)
+    eng.reset_cache()
+    a = eng.forward(prompt)[0, -1].float().cpu()
+    monkeypatch.setenv("B200_PREFILL_CHUNK", "2048")
+    eng.reset_cache()
+    b = eng.forward(prompt)[0, -1].float().cpu()
+    assert float((a - b).abs().max()) <= 2e-2 and float((a - b).abs().mean()) <= 2e-3
+    eng.close()

@@ -665,10 +665,17 @@ static int prefill_chunk(b200_engine* e, const int64_t* ids, int S, int p0, bool
 // whole prompt through the GEMM path, then lm_head + argmax for the last position
 static int engine_prefill(b200_engine* e, const int64_t* ids, int64_t S, cudaStream_t st) {
   int rc;
-  if ((rc = prefill_workspace(e, (int)std::min<int64_t>(S, kPrefillChunk))) != B200_OK) return rc;
+  // tokens per pass through the layers: B200_PREFILL_CHUNK (multiple of 128, 128 … 8192) overrides the default — bigger
+  // chunks give the o_proj / down_proj GEMMs more than 64 tiles for 148 SMs at the price of a bigger workspace
+  int chunk = kPrefillChunk;
+  if (const char* env = std::getenv("B200_PREFILL_CHUNK")) {
+    const int v = std::atoi(env);
+    if (v >= 128 && v <= 8192 && v % 128 == 0) chunk = v;
+  }
+  if ((rc = prefill_workspace(e, (int)std::min<int64_t>(S, chunk))) != B200_OK) return rc;
   const int p_start = (int)e->h_pos;
-  for (int64_t t0 = 0; t0 < S; t0 += kPrefillChunk) {
-    const int Sc = (int)std::min<int64_t>(kPrefillChunk, S - t0);
+  for (int64_t t0 = 0; t0 < S; t0 += chunk) {
+    const int Sc = (int)std::min<int64_t>(chunk, S - t0);
     if ((rc = prefill_chunk(e, ids + t0, Sc, p_start + (int)t0, t0 + Sc == S, st)) != B200_OK) return rc;
   }
   // the head's argmax advances pos by one: park it on the last prompt position first

@@ -20,6 +20,9 @@
 #include "common.cuh"
 #include "ops.cuh"
 
+#include <algorithm>
+#include <cstdlib>
+
 namespace b200 {
 
 namespace {
@@ -183,11 +186,165 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 }
 
+// ------------------------------------------------------------------------------------------------ persistent variant
+// Opt-in (B200_GEMM=persistent) until it has run against the oracle on hardware.  Same roles and the same verified
+// descriptors / TMEM access shapes as gemm_tcgen05_kernel, re-arranged for throughput:
+//   * 128 × 256 output tiles (one tcgen05.mma is M128 N256 K16): per 64-wide k-block the MMA pipe is busy 512 cycles
+//     and reads 48 KB of shared memory (96 B/clk; the 128 × 128 tile sits exactly on the 128 B/clk limit),
+//   * persistent CTAs (grid = min(tiles, #SMs)) walking tiles m-fastest, so concurrently running CTAs share weight rows
+//     in L2 and barrier init / TMEM allocation are paid once per CTA instead of once per tile,
+//   * the fp32 accumulator is double-buffered in TMEM (2 × 256 of the 512 columns): the epilogue of tile i drains
+//     buffer i & 1 while the MMA warp already accumulates tile i + 1 (tmem_full / tmem_empty barriers).
+constexpr int kPBN = 256;
+constexpr int kPStages = 4;
+constexpr int kPTileA = kBM * kBK * 2;    // 16 KB
+constexpr int kPTileB = kPBN * kBK * 2;   // 32 KB
+constexpr int kPTmemCols = 512;
+constexpr int kPGemmSmem = kPStages * (kPTileA + kPTileB) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t kPIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kPBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                               __nv_bfloat16* __restrict__ C, int M, int N, int K) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                                   // [stages][128 × 64 bf16]
+  uint8_t* sB = smem + kPStages * kPTileA;              // [stages][256 × 64 bf16]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kPStages * (kPTileA + kPTileB));
+  uint64_t* empty = full + kPStages;
+  uint64_t* tmem_full = empty + kPStages;               // [2]
+  uint64_t* tmem_empty = tmem_full + 2;                 // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = (M + kBM - 1) / kBM, nt = (N + kPBN - 1) / kPBN;
+  const int tiles = mt * nt;
+  const int kblocks = (K + kBK - 1) / kBK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < kPStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 128);   // every epilogue thread arrives once it holds its part of the tile in registers
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kPTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 1;
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int m0 = (t % mt) * kBM, n0 = (t / mt) * kPBN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty[s], ph);
+          mbar_arrive_expect_tx(&full[s], kPTileA + kPTileB);
+          tma_load_2d(sA + s * kPTileA, &tmap_a, kb * kBK, m0, &full[s]);
+          tma_load_2d(sB + s * kPTileB, &tmap_b, kb * kBK, n0, &full[s]);
+          if (++s == kPStages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      int i = 0;
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++i) {
+        const int acc = i & 1;
+        mbar_wait(&tmem_empty[acc], (uint32_t)(((i >> 1) & 1) ^ 1));   // the epilogue drained this buffer's last use
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kPBN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + s * kPTileA), b_addr = smem_u32(sB + s * kPTileB);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k)
+            umma_bf16(tmem_d, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), kPIdesc,
+                      (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty[s]);
+          if (++s == kPStages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------------------------------------- epilogue
+    const int q = warp & 3;
+    int i = 0;
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++i) {
+      const int acc = i & 1;
+      const int m0 = (t % mt) * kBM, n0 = (t / mt) * kPBN;
+      mbar_wait(&tmem_full[acc], (uint32_t)((i >> 1) & 1));
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < kPBN; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kPBN + c), r);
+        if (row < M && n0 + c < N) {
+          __nv_bfloat16* dst = C + (size_t)row * N + n0 + c;
+          if (n0 + c + 16 <= N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+            uint4 o0, o1;
+            o0.x = pack2(__uint_as_float(r[0]), __uint_as_float(r[1]));
+            o0.y = pack2(__uint_as_float(r[2]), __uint_as_float(r[3]));
+            o0.z = pack2(__uint_as_float(r[4]), __uint_as_float(r[5]));
+            o0.w = pack2(__uint_as_float(r[6]), __uint_as_float(r[7]));
+            o1.x = pack2(__uint_as_float(r[8]), __uint_as_float(r[9]));
+            o1.y = pack2(__uint_as_float(r[10]), __uint_as_float(r[11]));
+            o1.z = pack2(__uint_as_float(r[12]), __uint_as_float(r[13]));
+            o1.w = pack2(__uint_as_float(r[14]), __uint_as_float(r[15]));
+            reinterpret_cast<uint4*>(dst)[0] = o0;
+            reinterpret_cast<uint4*>(dst)[1] = o1;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (n0 + c + j < N) dst[j] = f_to_bf16(__uint_as_float(r[j]));
+          }
+        }
+      }
+      // all of this thread's tcgen05.ld have completed (tmem_ld16 waits): hand the buffer back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kPTmemCols) : "memory");
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_tmap_sw128(CUtensorMap* out, const void* base, int64_t rows, int64_t cols) {
+int make_tmap_sw128(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int box_rows = kBM) {
   void* p = nullptr;
   cudaDriverEntryPointQueryResult q;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
@@ -198,7 +355,7 @@ int make_tmap_sw128(CUtensorMap* out, const void* base, int64_t rows, int64_t co
   }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
-  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)kBM};
+  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = reinterpret_cast<EncodeTiledFn>(p)(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
                                                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -228,6 +385,26 @@ int launch_gemm_bf16(void* C, const void* A, const void* B, int64_t M, int64_t N
   }
   CUtensorMap ta, tb;
   int rc;
+  const char* mode = std::getenv("B200_GEMM");
+  if (mode != nullptr && mode[0] == 'p') {  // "persistent": opt-in, see gemm_tcgen05_persistent_kernel
+    static bool p_attr_set = false;
+    static int sms = 0;
+    if (!p_attr_set) {
+      B200_CUDA(cudaFuncSetAttribute(gemm_tcgen05_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPGemmSmem));
+      int dev = 0;
+      B200_CUDA(cudaGetDevice(&dev));
+      B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      p_attr_set = true;
+    }
+    if ((rc = make_tmap_sw128(&ta, A, M, K, kBM)) != B200_OK) return rc;
+    if ((rc = make_tmap_sw128(&tb, B, N, K, kPBN)) != B200_OK) return rc;
+    const int64_t tiles = ((M + kBM - 1) / kBM) * ((N + kPBN - 1) / kPBN);
+    g_launches.fetch_add(1);
+    gemm_tcgen05_persistent_kernel<<<(unsigned)std::min<int64_t>(tiles, sms), kGemmThreads, kPGemmSmem, st>>>(
+        ta, tb, (__nv_bfloat16*)C, (int)M, (int)N, (int)K);
+    B200_CUDA(cudaGetLastError());
+    return B200_OK;
+  }
   if ((rc = make_tmap_sw128(&ta, A, M, K)) != B200_OK) return rc;
   if ((rc = make_tmap_sw128(&tb, B, N, K)) != B200_OK) return rc;
   dim3 grid((unsigned)((N + kBN - 1) / kBN), (unsigned)((M + kBM - 1) / kBM));
