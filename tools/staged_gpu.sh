@@ -1,0 +1,47 @@
+#!/usr/bin/env bash
+# One GPU call that validates and measures everything that was STAGED without hardware:
+#   gpurun --timeout 1500 -- 'bash tools/staged_gpu.sh'
+# Results land in gpurun_out/staged/.  Nothing here changes a default; each block is independent (a failure does not
+# stop the next one) and bounded by its own timeout so a hang cannot eat the call.
+set -u
+cd "$(dirname "$0")/.."
+OUT=gpurun_out/staged
+mkdir -p "$OUT"
+python -m tinygpt_b200.build > "$OUT/build.log" 2>&1
+
+echo "== staged tests"
+B200_STAGED=1 timeout 900 python -m pytest tests/test_staged_gpu.py -m gpu -q -rA -s > "$OUT/staged_tests.log" 2>&1
+tail -n 25 "$OUT/staged_tests.log"
+
+echo "== grid-dependency microbenchmark"
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/sync_bench tools/micro/sync_bench.cu > "$OUT/sync_bench.log" 2>&1 \
+  && timeout 120 /tmp/sync_bench >> "$OUT/sync_bench.log" 2>&1
+cat "$OUT/sync_bench.log"
+
+echo "== decode: PDL (default) vs flag counters"
+for m in Qwen2.5-0.5B Llama-3.2-3B; do
+  timeout 400 python bench.py --model $m --steps 10 --warmup 3 --no-cpu-baseline > "$OUT/bench_${m}_pdl.json" 2> "$OUT/bench_${m}_pdl.err"
+  B200_FLAGSYNC=1 timeout 400 python bench.py --model $m --steps 10 --warmup 3 --no-cpu-baseline > "$OUT/bench_${m}_flagsync.json" 2> "$OUT/bench_${m}_flagsync.err"
+  python - "$OUT/bench_${m}_pdl.json" "$OUT/bench_${m}_flagsync.json" <<'PY'
+import json, sys
+for p in sys.argv[1:]:
+    try:
+        d = json.loads(open(p).read().strip().splitlines()[-1])
+        print(f"{p}: {d['value']:.0f} tok/s  {d['ms_per_token']*1e3:.1f} us/token  frac {d['roofline']['frac']:.3f}  e2e {d['e2e']['value']:.0f}")
+    except Exception as e:
+        print(p, "no result:", e)
+PY
+done
+B200_FLAGSYNC=1 timeout 200 python tools/trace_decode.py Qwen2.5-0.5B > "$OUT/trace_flagsync.log" 2>&1
+timeout 200 python tools/trace_decode.py Qwen2.5-0.5B > "$OUT/trace_pdl.log" 2>&1
+tail -n 8 "$OUT/trace_pdl.log" "$OUT/trace_flagsync.log"
+
+echo "== prefill (config 4): default / mma attention / + persistent GEMM / + one 2048-token chunk"
+timeout 300 python tools/prefill_bench.py > "$OUT/prefill_default.log" 2>&1
+B200_PREFILL_ATTN=mma timeout 300 python tools/prefill_bench.py > "$OUT/prefill_mma.log" 2>&1
+B200_PREFILL_ATTN=mma B200_GEMM=persistent timeout 300 python tools/prefill_bench.py > "$OUT/prefill_mma_pgemm.log" 2>&1
+B200_PREFILL_ATTN=mma B200_GEMM=persistent B200_PREFILL_CHUNK=2048 timeout 300 python tools/prefill_bench.py > "$OUT/prefill_mma_pgemm_chunk2048.log" 2>&1
+tail -n 1 "$OUT"/prefill_*.log
+echo "== GEMM alone"
+timeout 300 python tools/gemm_bench.py > "$OUT/gemm_bench.log" 2>&1
+cat "$OUT/gemm_bench.log"
