@@ -208,3 +208,26 @@ def test_prefill_chunk_override(built_lib, monkeypatch):
     b = eng.forward(prompt)[0, -1].float().cpu()
     assert float((a - b).abs().max()) <= 2e-2 and float((a - b).abs().mean()) <= 2e-3
     eng.close()
+
+
+# --------------------------------------------------------------------------------- loader fast path, CUDA destination
+def test_loader_cuda_staging_path(built_lib, tmp_path):
+    """The pinned-staging H2D path (chunked, strided column slices included) delivers the same bytes as the CPU path,
+    and the loaded tensors drive the engine to the same tokens as the in-memory synthetic checkpoint."""
+    from tinygpt_b200 import loader, tp
+    spec = models.TINY_QWEN2
+    w = models.synth_weights(spec, seed=9)
+    models.save_checkpoint(spec, w, str(tmp_path))
+    got_spec, got, _ = loader.load_checkpoint(tmp_path, device=DEV)
+    for k, v in w.items():
+        assert torch.equal(got[k].cpu().view(torch.int16), v.view(torch.int16)), k
+    _, r1, _ = loader.load_checkpoint(tmp_path, device=DEV, rank=1, world=2)
+    want = tp.shard_weights(spec, w, 1, 2)
+    for k, v in want.items():
+        assert torch.equal(r1[k].cpu().view(torch.int16), v.view(torch.int16)), k
+    prompt = [3, 1, 4, 1, 5, 9, 2, 6, 5]
+    a = engine.DecodeEngine(got_spec.with_ctx(128), got)
+    b = engine.DecodeEngine(spec.with_ctx(128), {k: v.to(DEV) for k, v in w.items()})
+    assert a.generate_sync(prompt, 16).tolist() == b.generate_sync(prompt, 16).tolist()
+    a.close()
+    b.close()
