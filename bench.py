@@ -355,7 +355,8 @@ def run_ours(args):
                    "l2": "weights 0.99 GB > 126 MB L2: re-streamed from HBM every token, no explicit flush",
                    "kernel_sync": ("per-op completion counters (B200_FLAGSYNC=1)"
                                    if os.environ.get("B200_FLAGSYNC") == "1" and world == 1 else
-                                   "programmatic dependent launch (griddepcontrol.wait)")},
+                                   "programmatic dependent launch (griddepcontrol.wait)"),
+                   "l2_prefetch_mb": int(os.environ.get("B200_L2PF_MB", "0") or 0)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src,
                      "kernel": f"whole decode token ({eng.launches_per_token} launches, PDL-chained; "

@@ -231,3 +231,29 @@ def test_loader_cuda_staging_path(built_lib, tmp_path):
     assert a.generate_sync(prompt, 16).tolist() == b.generate_sync(prompt, 16).tolist()
     a.close()
     b.close()
+
+
+# ------------------------------------------------------------------------------- cross-kernel L2 prefetch (B200_L2PF_MB)
+@pytest.mark.parametrize("flags", [{"B200_L2PF_MB": "16"}, {"B200_L2PF_MB": "24", "B200_FLAGSYNC": "1"}],
+                         ids=["l2pf", "l2pf+flagsync"])
+def test_l2_prefetch_changes_nothing_but_time(built_lib, flags, monkeypatch):
+    """The prefetch is a hint: ids must be identical with it on (full-size Qwen2.5-0.5B: the lm_head's 272 MB and the
+    per-layer matrices beyond the rings are prefetched by the preceding kernels; a bad address range would fault)."""
+    spec = models.QWEN25_05B.with_ctx(160)
+    prompt = torch.randint(0, spec.vocab, (16,), generator=torch.Generator().manual_seed(0))
+    runs = []
+    for on in (False, True):
+        for k, v in flags.items():
+            if on:
+                monkeypatch.setenv(k, v)
+            else:
+                monkeypatch.delenv(k, raising=False)
+        w = models.synth_weights(spec, seed=0, device=DEV, device_generator=True)
+        eng = engine.DecodeEngine(spec, w)
+        eng.reset_cache()
+        first = eng.gen_next_token(prompt.view(1, -1).to(DEV))
+        runs.append(torch.cat([first.view(-1), eng.decode(47)]).cpu())
+        torch.cuda.synchronize()
+        eng.close()
+        del w
+    assert torch.equal(runs[0], runs[1])

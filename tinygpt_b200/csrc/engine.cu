@@ -77,6 +77,8 @@ struct b200_engine {
   // async token pipeline (b200_engine_set_mailbox): ring in pinned host memory the argmax kernel posts tokens into
   unsigned long long* mailbox = nullptr;
   unsigned long long mailbox_cap = 1;
+  int64_t l2pf_bytes = 0;  // opt-in (B200_L2PF_MB): cross-kernel L2 prefetch budget per GEMV launch (gemv.cuh)
+  const void* head_w = nullptr;
   bool use_flagsync = false;
   unsigned long long* fs_ctr = nullptr;
   unsigned long long* fs_epoch = nullptr;
@@ -200,8 +202,10 @@ static int engine_launch_token(b200_engine* e, cudaStream_t st, bool with_head) 
   const size_t kv_layer = (size_t)d.max_ctx * e->Hkv_l * d.head_dim;
   int slot = 0;
   auto tr = [&]() -> unsigned long long* { return e->trace ? e->trace + 8 * (slot++) : nullptr; };
+  const bool pf = e->l2pf_bytes > 0;
   for (int l = 0; l < d.layers; ++l) {
     GemvPlan q = e->p_qkv[l];
+    if (pf) gemv_plan_prefetch(&q, e->p_o[l], e->lw[l].o_w, e->l2pf_bytes);
     q.p.trace = tr();
     q.p.fs = fs_next((unsigned int)q.grid);
     if ((rc = gemv_launch(q, st, pdl)) != B200_OK) return rc;
@@ -228,6 +232,10 @@ static int engine_launch_token(b200_engine* e, cudaStream_t st, bool with_head) 
     GemvPlan o = e->p_o[l], gu = e->p_gu[l];
     o.p.trace = tr();
     gu.p.trace = tr();
+    if (pf) {
+      gemv_plan_prefetch(&o, e->p_gu[l], e->lw[l].gate_up_w, e->l2pf_bytes);
+      gemv_plan_prefetch(&gu, e->p_down[l], e->lw[l].down_w, e->l2pf_bytes);
+    }
     o.p.fs = fs_next((unsigned int)o.grid);
     if ((rc = gemv_launch(o, st, pdl)) != B200_OK) return rc;
     gu.p.fs = fs_next((unsigned int)gu.grid);
@@ -237,6 +245,10 @@ static int engine_launch_token(b200_engine* e, cudaStream_t st, bool with_head) 
     const bool tp = e->tp_world > 1;
     dn.p.pos_inc = (last_node && !tp) ? e->pos : nullptr;  // the LAST kernel of a token advances the position
     dn.p.trace = tr();
+    if (pf) {
+      if (l + 1 < d.layers) gemv_plan_prefetch(&dn, e->p_qkv[l + 1], e->lw[l + 1].qkv_w, e->l2pf_bytes);
+      else if (with_head) gemv_plan_prefetch(&dn, e->p_head, e->head_w, e->l2pf_bytes);
+    }
     dn.p.fs = fs_next((unsigned int)dn.grid);
     if (fs && last_node) {  // full dependency instead of a poll; the only place a body-only token advances the epoch
       dn.p.fs.wait_ctr = nullptr;
@@ -247,6 +259,7 @@ static int engine_launch_token(b200_engine* e, cudaStream_t st, bool with_head) 
   if (with_head) {
     GemvPlan hd = e->p_head;
     hd.p.trace = tr();
+    if (pf) gemv_plan_prefetch(&hd, e->p_qkv[0], e->lw[0].qkv_w, e->l2pf_bytes);  // the next token starts there
     hd.p.fs = fs_next((unsigned int)hd.grid);
     if ((rc = gemv_launch(hd, st, pdl)) != B200_OK) return rc;
     int64_t* amax = reinterpret_cast<int64_t*>((uint8_t*)e->argmax_ws + argmax_workspace_bytes(1, e->V_l));
@@ -403,6 +416,9 @@ static int engine_build(const b200_model_desc* desc, const b200_weight_table* w,
   e->use_pdl = !(env && env[0] == '1');
   env = std::getenv("B200_FLAGSYNC");
   e->use_flagsync = (env && env[0] == '1') && world == 1 && e->use_pdl;
+  env = std::getenv("B200_L2PF_MB");
+  if (env) e->l2pf_bytes = (int64_t)std::max(0, std::min(64, std::atoi(env))) << 20;
+  e->head_w = w->lm_head;
   env = std::getenv("B200_NO_PREFILL_GEMM");
   e->use_prefill_gemm = !(env && env[0] == '1');
   e->final_norm_w = w->final_norm;

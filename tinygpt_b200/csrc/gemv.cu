@@ -109,6 +109,17 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
           }
         }
       }
+      // cross-kernel L2 prefetch (opt-in, gemv.cuh): queued behind this CTA's own last loads
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        if (p.pf_bytes[i] != 0) {
+          const char* a = static_cast<const char*>(p.pf_ptr[i]) + (size_t)blockIdx.x * p.pf_bytes[i];
+          for (unsigned int off = 0; off < p.pf_bytes[i]; off += 16384u) {
+            const unsigned int n = min(16384u, p.pf_bytes[i] - off);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a + off), "r"(n) : "memory");
+          }
+        }
+      }
     }
     return;
   }
@@ -532,6 +543,27 @@ int gemv_make_plan(GemvPlan* plan, const void* W, int64_t rows_total, int64_t n,
   B200_CHECK_ARG(plan->smem <= kGemvMaxSmem + 4096, "gemv: k=%lld needs %d bytes of shared memory", (long long)k,
                  plan->smem);
   return make_tmap_2d_bf16(&plan->tmap, W, rows_total, k, sh.box_r, kBoxK);
+}
+
+void gemv_plan_prefetch(GemvPlan* cur, const GemvPlan& next, const void* next_W, int64_t budget_bytes) {
+  cur->p.pf_bytes[0] = cur->p.pf_bytes[1] = 0;
+  cur->p.pf_ptr[0] = cur->p.pf_ptr[1] = nullptr;
+  if (budget_bytes <= 0 || next_W == nullptr || cur->grid <= 0) return;
+  const int box_r = 8 * next.rpw;
+  const int ksteps = next.p.k_pad / (kBoxK * kboxes(next.rpw, next.nseg));
+  // row blocks per CTA that next's ring holds completely; row blocks are dealt round-robin, so the rings of all CTAs
+  // together cover a contiguous PREFIX of the rows (of each segment)
+  const int64_t rb_cov = std::max<int64_t>(1, next.p.stages / std::max(1, ksteps));
+  const int64_t start_row = std::min<int64_t>(next.p.n, rb_cov * next.grid * box_r);
+  const int64_t row_bytes = (int64_t)next.p.k * 2;
+  const int64_t rows = std::min<int64_t>(next.p.n - start_row, budget_bytes / next.nseg / row_bytes);
+  if (rows <= 0) return;
+  const int64_t per_cta = (rows * row_bytes / cur->grid) / 128 * 128;   // whole lines; 16-byte aligned by construction
+  if (per_cta <= 0 || per_cta > (1ll << 30)) return;
+  for (int seg = 0; seg < next.nseg; ++seg) {
+    cur->p.pf_ptr[seg] = static_cast<const char*>(next_W) + ((int64_t)seg * next.p.seg_rows + start_row) * row_bytes;
+    cur->p.pf_bytes[seg] = (unsigned int)per_cta;
+  }
 }
 
 int gemv_launch(const GemvPlan& plan, cudaStream_t stream, bool pdl) {

@@ -35,6 +35,12 @@ struct GemvParams {
   int* pos_inc;                   // engine: when set, CTA 0 advances the token position after its last row block
   unsigned long long* epoch_inc;  // flag-sync engines: … and the count of completed tokens (with pos_inc)
   FlagSync fs;                    // opt-in flag synchronisation (common.cuh); fs.signal_ctr == null ⇒ plain PDL kernel
+  // opt-in cross-kernel L2 prefetch (B200_L2PF_MB): once this kernel's producer has issued its last TMA load it asks
+  // L2 for the part of the NEXT GEMV's weights that lies just beyond what that kernel's own rings hold, so that HBM
+  // keeps streaming through this kernel's tail, the kernel boundary and the next prologue.  Hint only: no effect on
+  // results.  CTA b prefetches [pf_ptr[i] + b·pf_bytes[i], + pf_bytes[i]); pf_bytes == 0 ⇒ nothing.
+  const void* pf_ptr[2];
+  unsigned int pf_bytes[2];
   // ---- tensor-parallel exchange (peer-mapped windows over NVLink).  Low-latency protocol: every fp32 partial travels
   // as ONE 8-byte store {value bits, tag} with tag = token epoch + 1, so data and "flag" arrive atomically together —
   // no system fence, no remote atomic, no separate flag poll (the idea of NCCL's LL protocol).
@@ -68,6 +74,9 @@ int gemv_make_plan(GemvPlan* plan, const void* W, int64_t rows_total, int64_t n,
                    int num_sms, int smem_budget = kGemvDefaultSmem);
 int gemv_smem_wanted(int64_t n, int64_t k, int nseg, int num_sms);
 int gemv_launch(const GemvPlan& plan, cudaStream_t stream, bool pdl);
+// Fill cur.p.pf_* so that `cur` prefetches into L2 what `next` (planned over weight matrix next_W) will stream right
+// after its rings are full: at most budget_bytes, starting at the first row block beyond the rings' coverage.
+void gemv_plan_prefetch(GemvPlan* cur, const GemvPlan& next, const void* next_W, int64_t budget_bytes);
 int gemv_setup_attributes();  // cudaFuncSetAttribute(max dynamic smem) for every instantiation, once per process
 
 }  // namespace b200

@@ -32,6 +32,23 @@ for p in sys.argv[1:]:
         print(p, "no result:", e)
 PY
 done
+echo "== decode: cross-kernel L2 prefetch (hint only) on the HBM-bound models"
+for m in Llama-3.2-3B Mistral-7B-v0.3; do
+  for mb in 8 24; do
+    B200_L2PF_MB=$mb timeout 400 python bench.py --model $m --steps 10 --warmup 3 --no-cpu-baseline > "$OUT/bench_${m}_l2pf${mb}.json" 2> "$OUT/bench_${m}_l2pf${mb}.err"
+  done
+  B200_L2PF_MB=24 B200_FLAGSYNC=1 timeout 400 python bench.py --model $m --steps 10 --warmup 3 --no-cpu-baseline > "$OUT/bench_${m}_l2pf24_flagsync.json" 2> "$OUT/bench_${m}_l2pf24_flagsync.err"
+done
+timeout 400 python bench.py --model Mistral-7B-v0.3 --steps 10 --warmup 3 --no-cpu-baseline > "$OUT/bench_Mistral-7B-v0.3_pdl.json" 2> "$OUT/bench_Mistral-7B-v0.3_pdl.err"
+python - "$OUT"/bench_*l2pf*.json "$OUT/bench_Mistral-7B-v0.3_pdl.json" <<'PY'
+import json, sys
+for p in sys.argv[1:]:
+    try:
+        d = json.loads(open(p).read().strip().splitlines()[-1])
+        print(f"{p}: {d['value']:.0f} tok/s  {d['ms_per_token']*1e3:.1f} us/token  frac {d['roofline']['frac']:.3f}")
+    except Exception as e:
+        print(p, "no result:", e)
+PY
 B200_FLAGSYNC=1 timeout 200 python tools/trace_decode.py Qwen2.5-0.5B > "$OUT/trace_flagsync.log" 2>&1
 timeout 200 python tools/trace_decode.py Qwen2.5-0.5B > "$OUT/trace_pdl.log" 2>&1
 tail -n 8 "$OUT/trace_pdl.log" "$OUT/trace_flagsync.log"
