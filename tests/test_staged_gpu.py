@@ -257,3 +257,58 @@ def test_l2_prefetch_changes_nothing_but_time(built_lib, flags, monkeypatch):
         eng.close()
         del w
     assert torch.equal(runs[0], runs[1])
+
+
+# --------------------------------------------------------------------- flag-sync + L2 prefetch on tensor-parallel engines
+def _tp_fs_worker(rank, world, port, spec_name, shard_attn, q):
+    import os
+    import torch.distributed as dist
+    from tinygpt_b200 import tp
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        spec = models.SPECS[spec_name]
+        if spec.max_ctx > 512:
+            spec = spec.with_ctx(256)
+        w = models.synth_weights(spec, seed=0)
+        prompt = torch.randint(0, spec.vocab, (1, 9), generator=torch.Generator().manual_seed(0)).to(dev)
+        out = []
+        for flags in ({}, {"B200_FLAGSYNC": "1", "B200_FLAGSYNC_TP": "1", "B200_L2PF_MB": "8"}):
+            for k in ("B200_FLAGSYNC", "B200_FLAGSYNC_TP", "B200_L2PF_MB"):
+                os.environ.pop(k, None)
+            os.environ.update(flags)
+            eng = tp.TPDecodeEngine(spec, w, rank, world, dev, shard_attn=shard_attn)
+            eng.reset_cache()
+            first = eng.gen_next_token(prompt)              # 8 body-only tokens + 1 head token, then 23 head tokens
+            toks = torch.cat([first.view(-1), eng.decode(23)]).cpu()
+            eng.reset_cache()
+            local = eng.forward(prompt)[0, -1].float().cpu()
+            out.append((toks, local))
+            dist.barrier()
+            eng.close()
+        if rank == 0:
+            q.put(out)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("spec_name,shard_attn", [("tiny-mistral", True), ("tiny-qwen2", False), ("Qwen2.5-0.5B", True)])
+def test_tp2_flagsync_bit_identical(built_lib, spec_name, shard_attn):
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_tp_fs_worker, args=(r, 2, port, spec_name, shard_attn, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    (toks_a, logits_a), (toks_b, logits_b) = q.get(timeout=200)
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    assert torch.equal(toks_a, toks_b) and torch.equal(logits_a, logits_b)

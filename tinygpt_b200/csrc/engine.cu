@@ -118,6 +118,7 @@ struct TpFinish {
   int gen_cap;
   int world;
   int with_head;
+  unsigned long long* fs_epoch_inc;  // flag-sync engines: tokens completed (this node has a full dependency)
 };
 __global__ void tp_finish_kernel(const TpFinish f) {
   pdl_trigger();
@@ -157,6 +158,7 @@ __global__ void tp_finish_kernel(const TpFinish f) {
   }
   *f.pos += 1;
   *f.epoch = ep + 1;
+  if (f.fs_epoch_inc != nullptr) *f.fs_epoch_inc += 1ull;
 }
 
 }  // namespace
@@ -250,7 +252,8 @@ static int engine_launch_token(b200_engine* e, cudaStream_t st, bool with_head) 
       else if (with_head) gemv_plan_prefetch(&dn, e->p_head, e->head_w, e->l2pf_bytes);
     }
     dn.p.fs = fs_next((unsigned int)dn.grid);
-    if (fs && last_node) {  // full dependency instead of a poll; the only place a body-only token advances the epoch
+    if (fs && last_node && !tp) {  // full dependency instead of a poll; the only place a body-only token advances the
+                                   // epoch (tensor parallel: tp_finish_kernel is the last node and does it)
       dn.p.fs.wait_ctr = nullptr;
       dn.p.epoch_inc = e->fs_epoch;
     }
@@ -294,6 +297,7 @@ static int engine_launch_token(b200_engine* e, cudaStream_t st, bool with_head) 
     f.gen_cap = e->gen_cap;
     f.world = e->tp_world;
     f.with_head = with_head ? 1 : 0;
+    f.fs_epoch_inc = fs ? e->fs_epoch : nullptr;
     B200_CUDA(launch_pdl(tp_finish_kernel, dim3(1), dim3(32), 0, st, false, f));  // last node: full dependency
   }
   return B200_OK;
@@ -415,7 +419,9 @@ static int engine_build(const b200_model_desc* desc, const b200_weight_table* w,
   env = std::getenv("B200_NO_PDL");
   e->use_pdl = !(env && env[0] == '1');
   env = std::getenv("B200_FLAGSYNC");
-  e->use_flagsync = (env && env[0] == '1') && world == 1 && e->use_pdl;
+  // tensor-parallel engines take it only when asked twice (B200_FLAGSYNC=1 B200_FLAGSYNC_TP=1): validate on one GPU first
+  const char* env_tp = std::getenv("B200_FLAGSYNC_TP");
+  e->use_flagsync = (env && env[0] == '1') && e->use_pdl && (world == 1 || (env_tp && env_tp[0] == '1'));
   env = std::getenv("B200_L2PF_MB");
   if (env) e->l2pf_bytes = (int64_t)std::max(0, std::min(64, std::atoi(env))) << 20;
   e->head_w = w->lm_head;

@@ -211,7 +211,9 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
             a.z += __uint_as_float(w1[r].x);
             a.w += __uint_as_float(w1[r].z);
           }
-        const uint2 rr = *reinterpret_cast<const uint2*>(p.tp_residual + 4 * i);
+        uint2 rr;  // hidden state stored by CTA 0 of an earlier, possibly still resident kernel: through L2 under FS
+        if constexpr (FS) rr = __ldcg(reinterpret_cast<const uint2*>(p.tp_residual + 4 * i));
+        else rr = *reinterpret_cast<const uint2*>(p.tp_residual + 4 * i);
         const __nv_bfloat162 r01 = *reinterpret_cast<const __nv_bfloat162*>(&rr.x);
         const __nv_bfloat162 r23 = *reinterpret_cast<const __nv_bfloat162*>(&rr.y);
         const __nv_bfloat162 h01 = __hadd2(r01, __floats2bfloat162_rn(a.x, a.y));
@@ -396,11 +398,17 @@ using KernelFn = void (*)(const GemvParams, const CUtensorMap);
 
 template <int RPW>
 KernelFn pick_kernel(int nseg, int pro, int epi, bool fs) {
-  if (fs) {  // the single-GPU engine's four launches per layer + lm_head
-    if (nseg == 2) return (pro == PRO_RMSNORM && epi == EPI_SILU_MUL)
-                              ? gemv_stream_kernel<RPW, 2, PRO_RMSNORM, EPI_SILU_MUL, true> : nullptr;
+  if (fs) {  // the engine's four launches per layer + lm_head, single GPU and tensor parallel
+    if (nseg == 2) {
+      if (epi != EPI_SILU_MUL) return nullptr;
+      if (pro == PRO_RMSNORM) return gemv_stream_kernel<RPW, 2, PRO_RMSNORM, EPI_SILU_MUL, true>;
+      if (pro == PRO_TP_RMSNORM) return gemv_stream_kernel<RPW, 2, PRO_TP_RMSNORM, EPI_SILU_MUL, true>;
+      return nullptr;
+    }
     if (pro == PRO_RMSNORM && epi == EPI_PLAIN) return gemv_stream_kernel<RPW, 1, PRO_RMSNORM, EPI_PLAIN, true>;
     if (pro == PRO_PLAIN && epi == EPI_RESIDUAL) return gemv_stream_kernel<RPW, 1, PRO_PLAIN, EPI_RESIDUAL, true>;
+    if (pro == PRO_TP_RMSNORM && epi == EPI_PLAIN) return gemv_stream_kernel<RPW, 1, PRO_TP_RMSNORM, EPI_PLAIN, true>;
+    if (pro == PRO_PLAIN && epi == EPI_TP_PUSH) return gemv_stream_kernel<RPW, 1, PRO_PLAIN, EPI_TP_PUSH, true>;
     return nullptr;
   }
   if (nseg == 2) {
