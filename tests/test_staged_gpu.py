@@ -312,3 +312,58 @@ def test_tp2_flagsync_bit_identical(built_lib, spec_name, shard_attn):
         p.join(timeout=30)
         assert p.exitcode == 0
     assert torch.equal(toks_a, toks_b) and torch.equal(logits_a, logits_b)
+
+
+# ------------------------------------------------------------------ register-resident small-k GEMV loop (B200_GEMV_SMALLK)
+@pytest.mark.parametrize("n,k,kind", [(1152, 896, "norm_bias"), (896, 896, "residual"), (4864, 896, "silu"),
+                                      (1152, 896, "norm"), (256, 896, "silu"), (40, 264, "residual"), (4000, 1024, "silu"),
+                                      (8, 8, "norm"), (5000, 512, "silu")])
+def test_smallk_gemv_is_bit_identical(built_lib, n, k, kind, monkeypatch):
+    """Same FMAs in the same order per row ⇒ the outputs must equal the default loop's bit for bit."""
+    from tinygpt_b200 import ops
+    g = torch.Generator().manual_seed(n + k)
+    x = torch.randn(k, generator=g).to(torch.bfloat16).to(DEV)
+    nw = (1 + 0.02 * torch.randn(k, generator=g)).to(torch.bfloat16).to(DEV)
+    rows = 2 * n if kind == "silu" else n
+    w = (0.02 * torch.randn(rows, k, generator=g)).to(torch.bfloat16).to(DEV)
+    vec = torch.randn(n, generator=g).to(torch.bfloat16).to(DEV)
+
+    def run():
+        if kind == "norm_bias":
+            return ops.gemv_fused(x, w, norm_weight=nw, eps=1e-6, bias=vec)
+        if kind == "norm":
+            return ops.gemv_fused(x, w, norm_weight=nw, eps=1e-6)
+        if kind == "residual":
+            return ops.gemv_fused(x, w, residual=vec)
+        return ops.gemv_fused(x, w, norm_weight=nw, eps=1e-6, silu_mul=True)
+
+    monkeypatch.delenv("B200_GEMV_SMALLK", raising=False)
+    base = run()
+    monkeypatch.setenv("B200_GEMV_SMALLK", "1")
+    got = run()
+    torch.cuda.synchronize()
+    assert torch.equal(got, base)
+
+
+@pytest.mark.parametrize("flags", [{"B200_GEMV_SMALLK": "1"}, {"B200_GEMV_SMALLK": "1", "B200_FLAGSYNC": "1"}],
+                         ids=["smallk", "smallk+flagsync"])
+def test_smallk_engine_bit_identical(built_lib, flags, monkeypatch):
+    for spec in (models.TINY_QWEN2, models.QWEN25_05B.with_ctx(160)):
+        prompt = torch.randint(0, spec.vocab, (6,), generator=torch.Generator().manual_seed(2))
+        runs = []
+        for on in (False, True):
+            for k, v in flags.items():
+                if on:
+                    monkeypatch.setenv(k, v)
+                else:
+                    monkeypatch.delenv(k, raising=False)
+            w = models.synth_weights(spec, seed=0, device=DEV, device_generator=True)
+            eng = engine.DecodeEngine(spec, w)
+            eng.reset_cache()
+            logits = eng.forward(prompt.view(1, -1).to(DEV), all_positions=True).float().cpu()
+            toks = eng.decode(20).cpu()
+            torch.cuda.synchronize()
+            eng.close()
+            del w
+            runs.append((logits, toks))
+        assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][1], runs[1][1]), spec.name

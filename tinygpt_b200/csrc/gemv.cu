@@ -54,7 +54,15 @@ __device__ __forceinline__ void st_volatile_u2(uint2* p, const uint2 v) {
 // FS = flag-synchronised variant (opt-in, B200_FLAGSYNC=1): the dependency on the producer kernel is a completion
 // counter polled by one thread (common.cuh FlagSync) instead of griddepcontrol.wait, activations are read through L2
 // (ld.global.cg) and the CTA counts itself done at the end.  FS = false compiles to the PDL kernel unchanged.
-template <int RPW, int NSEG, int PRO, int EPI, bool FS>
+// SMALLK = opt-in consumer loop (B200_GEMV_SMALLK=1) for the latency-bound small-k matrices (k_pad ≤ 1024, RPW 1, at
+// most kSmallkMaxRb row blocks per CTA: Qwen2.5-0.5B's qkv / o_proj / gate|up).  When the dependency resolves, all of
+// the CTA's weights already sit in the ring, so the job is to drain shared memory as fast as possible: the activation
+// vector lives in REGISTERS (32 fp32 per lane, read from shared memory once instead of once per row block and warp),
+// all row blocks are accumulated before any reduction, the xor-shuffle trees of all rows are interleaved, and lane j
+// finishes row block j so that the epilogues (SiLU, residual, store) of all row blocks run side by side.  The FMAs of a
+// row are issued in exactly the order of the default loop ⇒ bit-identical results.
+constexpr int kSmallkMaxRb = 6;
+template <int RPW, int NSEG, int PRO, int EPI, bool FS, bool SMALLK = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap) {
   constexpr int kBoxR = kNW * RPW;
@@ -110,10 +118,11 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
         }
       }
       // cross-kernel L2 prefetch (opt-in, gemv.cuh): queued behind this CTA's own last loads
-#pragma unroll
+#pragma unroll 1
       for (int i = 0; i < 2; ++i) {
         if (p.pf_bytes[i] != 0) {
           const char* a = static_cast<const char*>(p.pf_ptr[i]) + (size_t)blockIdx.x * p.pf_bytes[i];
+#pragma unroll 1
           for (unsigned int off = 0; off < p.pf_bytes[i]; off += 16384u) {
             const unsigned int n = min(16384u, p.pf_bytes[i] - off);
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a + off), "r"(n) : "memory");
@@ -294,7 +303,101 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
   int s = 0;
   uint32_t ph = 0;
   const uint8_t* const my_rows = stage_base + (size_t)(warp * RPW) * kRowBytes + lane * 16;
-  for (int i = 0; i < my_rbs; ++i) {
+  if constexpr (SMALLK) {
+    static_assert(RPW == 1 && (EPI == EPI_PLAIN || EPI == EPI_RESIDUAL || EPI == EPI_SILU_MUL), "SMALLK: RPW 1 only");
+    constexpr int kMaxBox = 4;               // k_pad ≤ 1024
+    constexpr int kKsMax = kMaxBox / KB;     // k steps per row block at most
+    float xf[kMaxBox][8];
+#pragma unroll
+    for (int b = 0; b < kMaxBox; ++b) {
+      if (b * kBoxK < p.k_pad) {
+        unpack8(*reinterpret_cast<const uint4*>(xs + b * kBoxK + lane * 8), xf[b]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) xf[b][e] = 0.f;
+      }
+    }
+    // lane j finishes row block j of this CTA: its epilogue operand is requested before the k loops
+    const int my_row = ((int)blockIdx.x + lane * (int)gridDim.x) * kBoxR + warp;
+    const bool my_valid = lane < my_rbs && my_row < p.n;
+    __nv_bfloat16 res_v = f_to_bf16(0.f);
+    if constexpr (EPI == EPI_RESIDUAL) {
+      if (my_valid) {
+        if constexpr (FS) res_v = __ldcg(p.residual + my_row);
+        else res_v = p.residual[my_row];
+      }
+    }
+    if constexpr (EPI == EPI_PLAIN) {
+      if (p.bias != nullptr && my_valid) bias_v = p.bias[my_row];
+    }
+    float acc[kSmallkMaxRb][NSEG], acc_b[kSmallkMaxRb][NSEG];
+#pragma unroll
+    for (int i = 0; i < kSmallkMaxRb; ++i)
+#pragma unroll
+      for (int seg = 0; seg < NSEG; ++seg) acc[i][seg] = acc_b[i][seg] = 0.f;
+#pragma unroll
+    for (int i = 0; i < kSmallkMaxRb; ++i) {
+      if (i < my_rbs) {
+#pragma unroll
+        for (int ks = 0; ks < kKsMax; ++ks) {
+          if (ks < ksteps) {
+            mbar_wait(&full[s], ph);
+            const uint8_t* st = my_rows + (size_t)s * kStageBytes;
+            uint4 wv[KB][NSEG];
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+              for (int seg = 0; seg < NSEG; ++seg)
+                wv[kb][seg] = *reinterpret_cast<const uint4*>(st + (kb * NSEG + seg) * kBoxBytes);
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+              for (int seg = 0; seg < NSEG; ++seg) dot8x2(wv[kb][seg], xf[ks * KB + kb], acc[i][seg], acc_b[i][seg]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+            if (++s == p.stages) {
+              s = 0;
+              ph ^= 1;
+            }
+          }
+        }
+      }
+    }
+    // all rows reduced together: independent shuffle chains interleave
+#pragma unroll
+    for (int i = 0; i < kSmallkMaxRb; ++i)
+#pragma unroll
+      for (int seg = 0; seg < NSEG; ++seg) acc[i][seg] += acc_b[i][seg];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int i = 0; i < kSmallkMaxRb; ++i)
+#pragma unroll
+        for (int seg = 0; seg < NSEG; ++seg) acc[i][seg] += __shfl_xor_sync(0xffffffffu, acc[i][seg], o);
+    float a0 = acc[0][0], a1 = acc[0][NSEG - 1];
+#pragma unroll
+    for (int j = 1; j < kSmallkMaxRb; ++j) {
+      if (lane == j) {
+        a0 = acc[j][0];
+        a1 = acc[j][NSEG - 1];
+      }
+    }
+    if (my_valid) {
+      if constexpr (EPI == EPI_PLAIN) {
+        __nv_bfloat16 v = f_to_bf16(a0);
+        if (p.bias != nullptr) v = __hadd(v, bias_v);
+        p.y[my_row] = v;
+      } else if constexpr (EPI == EPI_RESIDUAL) {
+        p.y[my_row] = __hadd(res_v, f_to_bf16(a0));
+      } else {  // EPI_SILU_MUL
+        const float g = round_bf16(a0);
+        const __nv_bfloat16 sg = f_to_bf16(g / (1.f + expf(-g)));
+        p.y[my_row] = __hmul(sg, f_to_bf16(a1));
+      }
+    }
+  }
+  const int loop_rbs = SMALLK ? 0 : my_rbs;  // the default loop below; SMALLK has done everything above
+  for (int i = 0; i < loop_rbs; ++i) {
     const int row_base = ((int)blockIdx.x + i * (int)gridDim.x) * kBoxR + warp * RPW;
     // operands of the epilogue are requested now so that their latency hides behind the k loop
     __nv_bfloat16 res_v = f_to_bf16(0.f);
@@ -396,6 +499,18 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
 // ------------------------------------------------------------------------------------------------------ dispatch
 using KernelFn = void (*)(const GemvParams, const CUtensorMap);
 
+// SMALLK instantiations: RPW 1, the single-GPU engine's three k = H launches
+KernelFn pick_smallk(int nseg, int pro, int epi, bool fs) {
+#define B200_SK(N, P, E)                                                                       \
+  if (nseg == N && pro == P && epi == E)                                                       \
+    return fs ? gemv_stream_kernel<1, N, P, E, true, true> : gemv_stream_kernel<1, N, P, E, false, true>;
+  B200_SK(1, PRO_RMSNORM, EPI_PLAIN)
+  B200_SK(1, PRO_PLAIN, EPI_RESIDUAL)
+  B200_SK(2, PRO_RMSNORM, EPI_SILU_MUL)
+#undef B200_SK
+  return nullptr;
+}
+
 template <int RPW>
 KernelFn pick_kernel(int nseg, int pro, int epi, bool fs) {
   if (fs) {  // the engine's four launches per layer + lm_head, single GPU and tensor parallel
@@ -431,7 +546,8 @@ KernelFn pick_kernel(int nseg, int pro, int epi, bool fs) {
   return nullptr;
 }
 
-KernelFn pick(int rpw, int nseg, int pro, int epi, bool fs = false) {
+KernelFn pick(int rpw, int nseg, int pro, int epi, bool fs = false, bool smallk = false) {
+  if (smallk) return rpw == 1 ? pick_smallk(nseg, pro, epi, fs) : nullptr;
   switch (rpw) {
     case 1: return pick_kernel<1>(nseg, pro, epi, fs);
     case 2: return pick_kernel<2>(nseg, pro, epi, fs);
@@ -451,8 +567,8 @@ int gemv_setup_attributes() {
       for (int nseg = 1; nseg <= 2; ++nseg)
         for (int pro = 0; pro < 3; ++pro)
           for (int epi = 0; epi < 4; ++epi)
-            for (int fs = 0; fs < 2; ++fs) {
-            KernelFn f = pick(rpw, nseg, pro, epi, fs != 0);
+            for (int fs = 0; fs < 4; ++fs) {
+            KernelFn f = pick(rpw, nseg, pro, epi, (fs & 1) != 0, (fs & 2) != 0);
             if (!f) continue;
             cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemvMaxSmem + 4096);
             // one carveout for every kernel of the token: a change of carveout between launches drains the SM and
@@ -547,6 +663,10 @@ int gemv_make_plan(GemvPlan* plan, const void* W, int64_t rows_total, int64_t n,
   plan->p.rowblocks = (int)sh.rbs;
   plan->p.stages = stages;
   plan->p.tp_world = 1;
+  // opt-in register-resident small-k consumer loop (see gemv_stream_kernel SMALLK)
+  const char* sk = std::getenv("B200_GEMV_SMALLK");
+  plan->smallk = sk != nullptr && sk[0] == '1' && sh.rpw == 1 && sh.k_pad <= 1024 && ctas_per_sm == 1 &&
+                 (sh.rbs + g - 1) / g <= kSmallkMaxRb && pick_smallk(nseg, pro, epi, false) != nullptr;
   B200_CHECK_ARG(pick(sh.rpw, nseg, pro, epi) != nullptr, "gemv: no kernel for nseg=%d pro=%d epi=%d", nseg, pro, epi);
   B200_CHECK_ARG(plan->smem <= kGemvMaxSmem + 4096, "gemv: k=%lld needs %d bytes of shared memory", (long long)k,
                  plan->smem);
@@ -576,7 +696,8 @@ void gemv_plan_prefetch(GemvPlan* cur, const GemvPlan& next, const void* next_W,
 
 int gemv_launch(const GemvPlan& plan, cudaStream_t stream, bool pdl) {
   const bool fs = plan.p.fs.signal_ctr != nullptr || plan.p.fs.wait_ctr != nullptr;
-  KernelFn f = pick(plan.rpw, plan.nseg, plan.pro, plan.epi, fs);
+  KernelFn f = plan.smallk ? pick(plan.rpw, plan.nseg, plan.pro, plan.epi, fs, true) : nullptr;
+  if (!f) f = pick(plan.rpw, plan.nseg, plan.pro, plan.epi, fs);
   if (!f) {
     set_error("gemv: no kernel instantiation (nseg=%d pro=%d epi=%d flag-sync=%d)", plan.nseg, plan.pro, plan.epi, (int)fs);
     return B200_ERR_INVALID;

@@ -62,6 +62,7 @@ struct GemvPlan {
   int epi;
   int grid;
   int smem;
+  bool smallk;  // opt-in (B200_GEMV_SMALLK=1): register-resident activation vector, batched reductions/epilogues
 };
 
 // Plan a GEMV over W[rows_total, k] (row-major bf16).  `n` = rows produced (per segment).

@@ -32,6 +32,21 @@ for p in sys.argv[1:]:
         print(p, "no result:", e)
 PY
 done
+echo "== decode 0.5B: register-resident small-k loop, alone and with flag counters"
+B200_GEMV_SMALLK=1 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > "$OUT/bench_Qwen2.5-0.5B_smallk.json" 2> "$OUT/bench_Qwen2.5-0.5B_smallk.err"
+B200_GEMV_SMALLK=1 B200_FLAGSYNC=1 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > "$OUT/bench_Qwen2.5-0.5B_smallk_flagsync.json" 2> "$OUT/bench_Qwen2.5-0.5B_smallk_flagsync.err"
+python - "$OUT"/bench_Qwen2.5-0.5B_smallk*.json <<'PY'
+import json, sys
+for p in sys.argv[1:]:
+    try:
+        d = json.loads(open(p).read().strip().splitlines()[-1])
+        print(f"{p}: {d['value']:.0f} tok/s  {d['ms_per_token']*1e3:.1f} us/token  frac {d['roofline']['frac']:.3f}")
+    except Exception as e:
+        print(p, "no result:", e)
+PY
+B200_GEMV_SMALLK=1 timeout 200 python tools/trace_decode.py Qwen2.5-0.5B > "$OUT/trace_smallk.log" 2>&1
+tail -n 8 "$OUT/trace_smallk.log"
+
 echo "== decode: cross-kernel L2 prefetch (hint only) on the HBM-bound models"
 for m in Llama-3.2-3B Mistral-7B-v0.3; do
   for mb in 8 24; do
