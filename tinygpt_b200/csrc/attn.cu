@@ -189,6 +189,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnDec
   }
   cp_async_wait_all();
   __syncthreads();
+  if (p.trace != nullptr && hg == 0 && split == 0 && tid == 0) p.trace[3] = global_timer_ns();  // q/k/v staged
 
   // ---- scores: LPK lanes cooperate on one key row, all G query heads at once
   {
@@ -213,6 +214,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnDec
     }
   }
   __syncthreads();
+  if (p.trace != nullptr && hg == 0 && split == 0 && tid == 0) p.trace[4] = global_timer_ns();  // scores done
 
   // ---- softmax inside the split (base-2 exponent like the reference): warp g owns head g
   for (int g = warp; g < G; g += kAttnWarps) {
@@ -234,6 +236,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnDec
     }
   }
   __syncthreads();
+  if (p.trace != nullptr && hg == 0 && split == 0 && tid == 0) p.trace[5] = global_timer_ns();  // softmax done
 
   // ---- P·V: thread = (key slot, 16-byte piece of the V row); G×8 fp32 accumulators
   {

@@ -48,6 +48,10 @@ for r in rows:
     prev_exit = r[4]
 print("avg per kernel type: wait-before-dependency, body, gap(prev exit -> my wait return)")
 for k, (c, wt, bd, gp, pr, f4, f5, f6) in agg.items():
+    if k == "attn":  # slots 3-5 of the attention kernel: q/k/v staged, scores done, softmax done (after the wait)
+        print(f"  {k:5s} x{c:3d}: wait {wt/c:6.2f} us  body {bd/c:6.2f} us (q/k/v staged {pr/c:5.2f}, scores {f4/c:5.2f}, "
+              f"softmax {f5/c:5.2f}, P.V = body end)  gap {gp/c:6.2f} us")
+        continue
     print(f"  {k:5s} x{c:3d}: wait {wt/c:6.2f} us  body {bd/c:6.2f} us (x ready {pr/c:5.2f}, 1st stage {f4/c:5.2f}, "
           f"1st block summed {f5/c:5.2f}, stored {f6/c:5.2f})  gap {gp/c:6.2f} us")
 print(f"token span {rows[-1][4]:.1f} us")
