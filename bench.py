@@ -195,6 +195,32 @@ def time_kernel_isolated(fn, iters=20, warm=3):
     return ts[len(ts) // 2]
 
 
+def reference_cuda_baseline(spec, weights):
+    """Decode tokens/s of the reference's own CUDA build (TinyTorch ops + cuBLAS + TinyFA, ≈ 490 launches per token) on
+    this GPU, same model shape / synthetic weights / prompt length / 128 timed greedy steps.  Never fatal: any failure
+    is reported as {"unavailable": why}.  Bounded: checkpoint write + load + 16-token prefill + 128 steps."""
+    import tempfile
+    bin_path = ROOT / "oracle" / "_ref" / "ref_cuda_decode"
+    if not bin_path.exists():
+        return None
+    try:
+        import torch
+        sys.path.insert(0, str(ROOT / "tools"))
+        import ref_cuda_parity as rp
+        from tinygpt_b200 import models
+        prompt = torch.randint(0, spec.vocab, (PROMPT_LEN,), generator=torch.Generator().manual_seed(0)).tolist()
+        with tempfile.TemporaryDirectory() as td:
+            models.save_checkpoint(spec, weights, td)
+            _, _, timing = rp.run_reference(spec, td, prompt, 2, time_steps=NEW_TOKENS)
+        if not timing:
+            return {"unavailable": "ref_cuda_decode printed no timing line"}
+        return {"value": timing["tokens_per_s"], "unit": "tokens/s", "us_per_token": timing["us_per_token"],
+                "kind": "reference CUDA build (unmodified sources, oracle/_ref/ref_cuda_decode), same GPU",
+                "sample": f"{NEW_TOKENS} greedy decode steps after a {PROMPT_LEN}-token prompt, device-resident token loop"}
+    except Exception as e:  # noqa: BLE001 — a baseline must never take the bench line down
+        return {"unavailable": f"{type(e).__name__}: {str(e)[:300]}"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -339,6 +365,13 @@ def run_ours(args):
         v, sample = ref.step(8)
         cpu = {"value": v, "unit": "tokens/s", "cores": ref.cores, "kind": ref.kind, "sample": sample}
 
+    # ---- the reference's OWN CUDA path on this GPU (a reported baseline like cpu_baseline; rank 0, N = 1 only): the
+    # unmodified reference compiled from /root/reference into oracle/_ref/ref_cuda_decode (make -C oracle cuda), run
+    # as a separate process on the same synthetic checkpoint shape, AFTER every measurement of ours
+    ref_cuda = None
+    if world == 1 and not args.no_cpu_baseline and os.environ.get("B200_BENCH_NO_REF_CUDA") != "1":
+        ref_cuda = reference_cuda_baseline(spec, w)
+
     line = {
         "metric": "decode tokens/sec (bf16, batch=1)", "value": value, "unit": "tokens/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
@@ -372,6 +405,8 @@ def run_ours(args):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if ref_cuda is not None:
+        line["reference_cuda_baseline"] = ref_cuda
     print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:

@@ -1,0 +1,199 @@
+// ref_cuda_main.cpp — TEST INFRASTRUCTURE.  Runs the UNMODIFIED reference's CUDA path (keith2018/TinyGPT: its modules,
+// TinyTorch CUDA ops, cuBLAS GEMMs, TinyFA attention, its KV-cache manager and its own argmax), compiled from
+// /root/reference by `make -C oracle cuda`, on a checkpoint directory written by tinygpt_b200.models.save_checkpoint:
+// the bf16 parity oracle north_star names ("logits matching the reference CUDA path … bit-exact argmax ids") and the
+// reference's own decode speed on the same GPU.  Nothing in the product links or loads this.
+//
+//   ref_cuda_decode --ckpt DIR --family {llama|qwen2|qwen3|mistral} --dims H,L,Hq,Hkv,hd,I,V,ctx --theta T --eps E
+//                   --tie {0|1} [--rope-scaling f,hi,lo,orig] --ids FILE(int64) --new N [--forced FILE(int64)]
+//                   --out FILE [--time-steps K]
+// Output file: int64 N tokens, then float32 [N, V] logits (last position of the prefill, then every decode step).
+// With --forced the decode steps consume the given tokens (teacher forcing) instead of the reference's own argmax.
+// The loop is GPTEngine::generateSync's (src/engine/GPTEngine.cpp:154-174): genNextToken = forward → narrow last →
+// Sampler greedy = function::argmax(logits, -1, true) (src/engine/Sampler.cpp:23-29).
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include <unistd.h>
+
+#include <cuda_runtime.h>
+
+#include "Functions.h"
+#include "Modules.h"
+#include "model/ModelLlama.h"
+#include "model/ModelMistral.h"
+#include "model/ModelQwen2.h"
+#include "model/ModelQwen3.h"
+
+namespace tt = tinytorch;
+namespace hf = tinygpt::huggingface::model;
+
+static std::vector<int64_t> readI64(const std::string& path) {
+  std::vector<int64_t> v;
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return v;
+  fseek(f, 0, SEEK_END);
+  const long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  v.resize(n / 8);
+  if (fread(v.data(), 8, v.size(), f) != v.size()) v.clear();
+  fclose(f);
+  return v;
+}
+
+static std::vector<double> parseList(const char* s) {
+  std::vector<double> v;
+  const char* p = s;
+  while (*p) {
+    char* e;
+    v.push_back(strtod(p, &e));
+    if (e == p) break;
+    p = (*e == ',') ? e + 1 : e;
+  }
+  return v;
+}
+
+static void fillCommon(hf::ModelConfig& c, const std::vector<double>& d, float eps, bool tie) {
+  c.torchDtype = tt::DType::BFloat16;
+  c.hiddenSize = (int64_t)d[0];
+  c.numHiddenLayers = (int64_t)d[1];
+  c.numAttentionHeads = (int64_t)d[2];
+  c.numKeyValueHeads = (int64_t)d[3];
+  c.intermediateSize = (int64_t)d[5];
+  c.vocabSize = (int64_t)d[6];
+  c.maxPositionEmbeddings = (int64_t)d[7];
+  c.rmsNormEps = eps;
+  c.tieWordEmbeddings = tie;
+  c.bosTokenId = 0;
+  c.eosTokenId = 0;
+}
+
+int main(int argc, char** argv) {
+  std::string ckpt, family, idsPath, forcedPath, outPath;
+  std::vector<double> dims, rs;
+  float theta = 10000.f, eps = 1e-5f;
+  int tie = 1, nNew = 8, timeSteps = 0;
+  for (int i = 1; i + 1 < argc; i += 2) {
+    const std::string a = argv[i];
+    const char* v = argv[i + 1];
+    if (a == "--ckpt") ckpt = v;
+    else if (a == "--family") family = v;
+    else if (a == "--dims") dims = parseList(v);
+    else if (a == "--theta") theta = (float)atof(v);
+    else if (a == "--eps") eps = (float)atof(v);
+    else if (a == "--tie") tie = atoi(v);
+    else if (a == "--rope-scaling") rs = parseList(v);
+    else if (a == "--ids") idsPath = v;
+    else if (a == "--forced") forcedPath = v;
+    else if (a == "--new") nNew = atoi(v);
+    else if (a == "--out") outPath = v;
+    else if (a == "--time-steps") timeSteps = atoi(v);
+  }
+  if (ckpt.empty() || dims.size() != 8 || idsPath.empty() || outPath.empty()) {
+    fprintf(stderr, "usage: see the header of oracle/ref_cuda_main.cpp\n");
+    return 2;
+  }
+  tt::NoGradGuard guard;
+  tt::Device dev(tt::DeviceType::CUDA, 0);
+  hf::LlamaConfig llama;
+  hf::QwenConfig qwen;
+  hf::MistralConfig mistral;
+  std::unique_ptr<tinygpt::GPTModel> model;
+  if (family == "llama") {
+    fillCommon(llama, dims, eps, tie != 0);
+    llama.headDim = (int64_t)dims[4];
+    llama.attentionBias = false;
+    llama.ropeTheta = theta;
+    if (rs.size() == 4) llama.ropeScaling = {(float)rs[0], (float)rs[1], (float)rs[2], (int64_t)rs[3], "llama3"};
+    model = std::make_unique<tinygpt::ModelLlama>(llama, dev);
+  } else if (family == "qwen2" || family == "qwen3") {
+    fillCommon(qwen, dims, eps, tie != 0);
+    qwen.headDim = (int64_t)dims[4];
+    qwen.ropeTheta = theta;
+    qwen.slidingWindow = 0;
+    qwen.useSlidingWindow = false;
+    qwen.useMRope = false;
+    if (family == "qwen2") model = std::make_unique<tinygpt::ModelQwen2>(qwen, dev);
+    else model = std::make_unique<tinygpt::ModelQwen3>(qwen, dev);
+  } else if (family == "mistral") {
+    fillCommon(mistral, dims, eps, tie != 0);
+    mistral.ropeTheta = theta;
+    mistral.slidingWindow = 0;
+    mistral.useSlidingWindow = false;
+    model = std::make_unique<tinygpt::ModelMistral>(mistral, dev);
+  } else {
+    fprintf(stderr, "unknown family %s\n", family.c_str());
+    return 2;
+  }
+  // the reference's loader path: SafeTensors::load(model(), path, strict = false), then to(dtype), eval()
+  // (src/model/GPTModel.h:96, src/huggingface/ModelLoader.cpp:70-87)
+  if (!model->load(ckpt + "/model.safetensors")) {
+    fprintf(stderr, "reference loader failed on %s\n", ckpt.c_str());
+    return 3;
+  }
+  model->model().to(tt::DType::BFloat16);
+  model->model().eval();
+
+  const std::vector<int64_t> ids = readI64(idsPath);
+  const std::vector<int64_t> forced = forcedPath.empty() ? std::vector<int64_t>() : readI64(forcedPath);
+  if (ids.empty() || (!forcedPath.empty() && (int)forced.size() < nNew)) {
+    fprintf(stderr, "bad --ids / --forced\n");
+    return 2;
+  }
+  const int64_t V = (int64_t)dims[6];
+  const int64_t S = (int64_t)ids.size();
+  auto idsTensor = [&](const int64_t* p, int64_t n) {
+    tt::Tensor t = tt::Tensor::empty({1, n}, tt::Options(tt::Device(tt::DeviceType::CPU), tt::DType::Int64));
+    std::memcpy(t.dataPtr<int64_t>(), p, sizeof(int64_t) * n);
+    return t.to(dev);
+  };
+  std::vector<int64_t> tokens;
+  std::vector<float> logitsAll((size_t)nNew * V);
+  auto step = [&](const tt::Tensor& in, int64_t n, int k) {
+    tt::Tensor logits = model->forward(in);                                        // [1, n, V] bf16
+    tt::Tensor last = tt::function::narrow(logits, 1, n - 1, 1).squeeze(1);        // [1, V]
+    tt::Tensor next = tt::function::argmax(last, -1, true);                        // greedy sampler
+    tt::Tensor f = last.to(tt::DType::Float32).to(tt::Device(tt::DeviceType::CPU));
+    std::memcpy(logitsAll.data() + (size_t)k * V, f.dataPtr<float>(), sizeof(float) * V);
+    const int64_t tok = next.to(tt::Device(tt::DeviceType::CPU)).dataPtr<int64_t>()[0];
+    tokens.push_back(tok);
+    return tok;
+  };
+  model->resetCache();
+  int64_t tok = step(idsTensor(ids.data(), S), S, 0);
+  for (int k = 1; k < nNew; ++k) {
+    const int64_t in = forced.empty() ? tok : forced[k - 1];
+    tok = step(idsTensor(&in, 1), 1, k);
+  }
+  FILE* f = fopen(outPath.c_str(), "wb");
+  if (!f) return 4;
+  fwrite(tokens.data(), 8, tokens.size(), f);
+  fwrite(logitsAll.data(), 4, logitsAll.size(), f);
+  fclose(f);
+
+  if (timeSteps > 0) {
+    // the reference's generateSync decode loop, timed like bench.py times ours: device-resident token feeds the next
+    // step, no logits copy; one synchronisation at the end
+    model->resetCache();
+    tt::Tensor cur = tt::function::argmax(
+        tt::function::narrow(model->forward(idsTensor(ids.data(), S)), 1, S - 1, 1).squeeze(1), -1, true);
+    cudaDeviceSynchronize();
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int k = 0; k < timeSteps; ++k) {
+      tt::Tensor logits = model->forward(cur);
+      cur = tt::function::argmax(tt::function::narrow(logits, 1, 0, 1).squeeze(1), -1, true);
+    }
+    cudaDeviceSynchronize();
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    printf("{\"impl\": \"reference-cuda\", \"tokens_per_s\": %.3f, \"us_per_token\": %.2f, \"steps\": %d, \"prompt\": %lld}\n",
+           timeSteps / dt, dt / timeSteps * 1e6, timeSteps, (long long)S);
+  }
+  fflush(stdout);
+  _exit(0);  // skip static destructors (the reference's allocator asserts on teardown order)
+}

@@ -367,3 +367,39 @@ def test_smallk_engine_bit_identical(built_lib, flags, monkeypatch):
             del w
             runs.append((logits, toks))
         assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][1], runs[1][1]), spec.name
+
+
+# ------------------------------------------------------------- the reference's own CUDA path as the oracle (oracle/_ref)
+def test_engine_and_oracle_against_reference_cuda(built_lib):
+    """oracle/_ref/ref_cuda_decode = the UNMODIFIED reference CUDA build (TinyTorch ops + cuBLAS + TinyFA), compiled in
+    the container that has /root/reference (`make -C oracle cuda`).  Same synthetic checkpoint, same forced tokens:
+    engine vs reference and oracle vs reference within the summation-order floor (cuBLAS' order is not ours), greedy
+    ids equal wherever the reference's own top-2 margin is decisive."""
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    sys.path.insert(0, str(root / "tools"))
+    import ref_cuda_parity as rp
+    if not rp.REF_BIN.exists():
+        pytest.skip("oracle/_ref/ref_cuda_decode not built (needs /root/reference: make -C oracle cuda)")
+    import tempfile
+    for spec in (models.TINY_QWEN2, models.TINY_LLAMA, models.TINY_QWEN3, models.TINY_MISTRAL):
+        w = models.synth_weights(spec, seed=0)
+        prompt = torch.randint(0, spec.vocab, (16,), generator=torch.Generator().manual_seed(0)).tolist()
+        with tempfile.TemporaryDirectory() as td:
+            models.save_checkpoint(spec, w, td)
+            toks, logits, _ = rp.run_engine(spec, w, prompt, 16)
+            ref_toks, ref_logits, _ = rp.run_reference(spec, td, prompt, 16, forced=toks.tolist())
+        wf = {k: v.float() for k, v in w.items()}
+        _, logits_orc = orc.generate_greedy(to_oracle_cfg(spec), wf, torch.tensor(prompt), 16, models.rope_table(spec),
+                                            "bf16", forced=toks)
+        d_eng, d_orc = (logits - ref_logits).abs(), (logits_orc - ref_logits).abs()
+        top = float(ref_logits.abs().max())
+        ulp = 2.0 ** (torch.floor(torch.log2(torch.tensor(top))).item() - 7)
+        print(f"[{spec.name}] engine-vs-reference-CUDA mean {float(d_eng.mean()):.3e} max {float(d_eng.max()):.3e}; "
+              f"oracle-vs-reference-CUDA mean {float(d_orc.mean()):.3e} max {float(d_orc.max()):.3e}; ulp {ulp:.3e}")
+        assert float(d_orc.mean()) <= 4e-3 and float(d_orc.max()) <= 8 * ulp, "oracle's bf16 rounding points are off"
+        assert float(d_eng.mean()) <= 4e-3 and float(d_eng.max()) <= 8 * ulp
+        srt = torch.sort(ref_logits, dim=-1, descending=True).values
+        decided = (srt[:, 0] - srt[:, 1]) > 4 * ulp
+        assert torch.equal(ref_toks[decided], toks[decided]), f"{spec.name}: greedy ids differ on decisive steps"

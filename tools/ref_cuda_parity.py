@@ -1,0 +1,148 @@
+"""Engine and oracle against the REFERENCE'S OWN CUDA PATH on the same GPU (north_star: "logits matching the reference
+CUDA path within 1e-3 (bf16) / bit-exact for argmax token ids on the same prompts").
+
+oracle/_ref/ref_cuda_decode is the unmodified reference (TinyTorch CUDA ops + cuBLAS + TinyFA + its KV-cache manager +
+its argmax) compiled from /root/reference by `make -C oracle cuda` in the build container; it travels to the GPU box as
+a binary.  For every model this script
+  1. writes the seeded synthetic checkpoint in the reference loader's layout (models.save_checkpoint),
+  2. runs our engine (free-running greedy decode, then logits teacher-forced on its own tokens),
+  3. runs the reference CUDA path teacher-forced on the SAME tokens, and once free-running,
+  4. runs the CPU oracle teacher-forced on the same tokens (small models),
+and reports |engine − reference|, |oracle − reference| (this pins the oracle's bf16 rounding points, the one item that
+could not be pinned without a GPU), greedy-id agreement, and the reference's own decode speed next to ours.
+
+    python tools/ref_cuda_parity.py [--models tiny-qwen2,tiny-llama,tiny-qwen3,tiny-mistral,Qwen2.5-0.5B] [--new 24]
+                                    [--json gpurun_out/ref_cuda_parity.json]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import subprocess
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+from tinygpt_b200 import engine, models  # noqa: E402
+
+REF_BIN = ROOT / "oracle" / "_ref" / "ref_cuda_decode"
+FAMILY = {"llama": "llama", "qwen2": "qwen2", "qwen3": "qwen3", "mistral": "mistral"}
+
+
+def run_reference(spec, ckpt_dir, prompt, n_new, forced=None, time_steps=0):
+    """→ (tokens [n_new] int64, logits [n_new, V] float32, timing dict or None) from the reference CUDA binary."""
+    d = Path(ckpt_dir)
+    (d / "ids.bin").write_bytes(np.asarray(prompt, dtype=np.int64).tobytes())
+    cmd = [str(REF_BIN), "--ckpt", str(d), "--family", FAMILY[spec.model_type], "--dims",
+           ",".join(str(int(v)) for v in (spec.hidden, spec.layers, spec.q_heads, spec.kv_heads, spec.head_dim,
+                                          spec.intermediate, spec.vocab, spec.max_ctx)),
+           "--theta", repr(float(spec.rope_theta)), "--eps", repr(float(spec.rms_eps)), "--tie", str(int(spec.tie)),
+           "--ids", str(d / "ids.bin"), "--new", str(n_new), "--out", str(d / "ref_out.bin")]
+    if spec.rope_scaling is not None:
+        sc = spec.rope_scaling
+        cmd += ["--rope-scaling", f"{sc.factor},{sc.high_freq_factor},{sc.low_freq_factor},{sc.original_context_length}"]
+    if forced is not None:
+        (d / "forced.bin").write_bytes(np.asarray(forced, dtype=np.int64).tobytes())
+        cmd += ["--forced", str(d / "forced.bin")]
+    if time_steps:
+        cmd += ["--time-steps", str(time_steps)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=1200)
+    if r.returncode != 0:
+        raise RuntimeError(f"ref_cuda_decode failed ({r.returncode}): {r.stderr[-800:]}")
+    raw = (d / "ref_out.bin").read_bytes()
+    toks = np.frombuffer(raw[: 8 * n_new], dtype=np.int64).copy()
+    logits = np.frombuffer(raw[8 * n_new:], dtype=np.float32).reshape(n_new, spec.vocab).copy()
+    timing = None
+    for line in r.stdout.splitlines():
+        if line.startswith("{"):
+            timing = json.loads(line)
+    return torch.from_numpy(toks), torch.from_numpy(logits), timing
+
+
+def run_engine(spec, w, prompt, n_new):
+    dev = "cuda"
+    eng = engine.DecodeEngine(spec, {k: v.to(dev) for k, v in w.items()})
+    p = torch.tensor(prompt, dtype=torch.int64).view(1, -1).to(dev)
+    eng.reset_cache()
+    first = eng.gen_next_token(p)
+    toks = torch.cat([first.view(-1), eng.decode(n_new - 1)]).cpu()
+    eng.reset_cache()
+    logits = [eng.forward(p)[0, -1].float().cpu()]
+    for i in range(n_new - 1):
+        logits.append(eng.forward(toks[i].view(1, 1).to(dev))[0, -1].float().cpu())
+    # decode speed, device-resident loop (what bench.py times)
+    eng.reset_cache()
+    eng.gen_next_token(p)
+    n_time = min(128, spec.max_ctx - len(prompt) - 2)
+    eng.decode(4)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    eng.seek(len(prompt))
+    e0.record()
+    eng.decode(n_time)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / n_time
+    eng.close()
+    return toks, torch.stack(logits), us
+
+
+def compare(name, a, b):
+    d = (a - b).abs()
+    return {"pair": name, "mean_abs": float(d.mean()), "max_abs": float(d.max()),
+            "frac_bit_identical": float((a == b).float().mean()), "frac_within_1e-3": float((d <= 1e-3).float().mean())}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--models", default="tiny-qwen2,tiny-llama,tiny-qwen3,tiny-mistral,Qwen2.5-0.5B")
+    ap.add_argument("--new", type=int, default=24)
+    ap.add_argument("--prompt", type=int, default=16)
+    ap.add_argument("--json", default="")
+    args = ap.parse_args()
+    if not REF_BIN.exists():
+        raise SystemExit(f"{REF_BIN} is missing: build it in the container that has /root/reference (make -C oracle cuda)")
+    from helpers import orc, to_oracle_cfg
+    report = []
+    for name in args.models.split(","):
+        spec = models.SPECS[name]
+        if spec.max_ctx > 512:
+            spec = spec.with_ctx(256)
+        big = spec.hidden * spec.layers > 10000
+        w = models.synth_weights(spec, seed=0, device="cuda" if big else "cpu", device_generator=big)
+        prompt = torch.randint(0, spec.vocab, (args.prompt,), generator=torch.Generator().manual_seed(0)).tolist()
+        with tempfile.TemporaryDirectory() as td:
+            models.save_checkpoint(spec, w, td)
+            toks, logits, us = run_engine(spec, w, prompt, args.new)
+            ref_toks_forced, ref_logits, _ = run_reference(spec, td, prompt, args.new, forced=toks.tolist())
+            ref_toks_free, _, timing = run_reference(spec, td, prompt, args.new, time_steps=128 if big else 32)
+        row = {"model": name, "engine_vs_reference_cuda": compare("engine-ref", logits, ref_logits)}
+        # greedy ids: the reference's argmax on ITS logits, forced on our tokens, step by step
+        srt = torch.sort(ref_logits, dim=-1, descending=True).values
+        margin = (srt[:, 0] - srt[:, 1])
+        agree = (ref_toks_forced == toks)
+        row["greedy_ids"] = {"equal_steps": int(agree.sum()), "steps": int(len(toks)),
+                             "min_margin_where_different": float(margin[~agree].min()) if (~agree).any() else None,
+                             "free_running_identical_prefix": int((torch.cumprod((ref_toks_free == toks).long(), 0)).sum())}
+        if not big:
+            wf = {k: v.float().cpu() for k, v in w.items()}
+            _, logits_orc = orc.generate_greedy(to_oracle_cfg(spec), wf, torch.tensor(prompt), args.new,
+                                                models.rope_table(spec), "bf16", forced=toks)
+            row["oracle_vs_reference_cuda"] = compare("oracle-ref", logits_orc, ref_logits)
+            row["engine_vs_oracle"] = compare("engine-oracle", logits, logits_orc)
+        row["decode_us_per_token"] = {"ours": us, "reference_cuda": timing["us_per_token"] if timing else None}
+        report.append(row)
+        print(json.dumps(row), flush=True)
+    if args.json:
+        Path(args.json).parent.mkdir(parents=True, exist_ok=True)
+        Path(args.json).write_text(json.dumps(report, indent=1))
+
+
+if __name__ == "__main__":
+    main()

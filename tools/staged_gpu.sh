@@ -13,6 +13,14 @@ echo "== staged tests"
 B200_STAGED=1 timeout 900 python -m pytest tests/test_staged_gpu.py -m gpu -q -rA -s > "$OUT/staged_tests.log" 2>&1
 tail -n 25 "$OUT/staged_tests.log"
 
+echo "== engine and oracle against the reference's own CUDA path (oracle/_ref/ref_cuda_decode, if it was built)"
+if [ -x oracle/_ref/ref_cuda_decode ]; then
+  timeout 900 python tools/ref_cuda_parity.py --json "$OUT/ref_cuda_parity.json" > "$OUT/ref_cuda_parity.log" 2>&1
+  tail -n 12 "$OUT/ref_cuda_parity.log"
+else
+  echo "not built: run 'make -C oracle cuda' in the container that has /root/reference"
+fi
+
 echo "== grid-dependency microbenchmark"
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/sync_bench tools/micro/sync_bench.cu > "$OUT/sync_bench.log" 2>&1 \
   && timeout 120 /tmp/sync_bench >> "$OUT/sync_bench.log" 2>&1
