@@ -203,6 +203,20 @@ constexpr int kPTmemCols = 512;
 constexpr int kPGemmSmem = kPStages * (kPTileA + kPTileB) + 1024 /*align*/ + 256 /*barriers*/;
 constexpr uint32_t kPIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kPBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
 
+// mbarrier wait that traps after ~2 s instead of spinning forever: a protocol bug in this not-yet-run kernel must fail
+// the launch, not hang the GPU
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+  unsigned int spins = 0;
+  unsigned long long t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0xffffu) == 0) {
+      const unsigned long long now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 2000000000ull) __trap();
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                                __nv_bfloat16* __restrict__ C, int M, int N, int K) {
@@ -253,7 +267,7 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const
       for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
         const int m0 = (t % mt) * kBM, n0 = (t / mt) * kPBN;
         for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&empty[s], ph);
+          mbar_wait_bounded(&empty[s], ph);
           mbar_arrive_expect_tx(&full[s], kPTileA + kPTileB);
           tma_load_2d(sA + s * kPTileA, &tmap_a, kb * kBK, m0, &full[s]);
           tma_load_2d(sB + s * kPTileB, &tmap_b, kb * kBK, n0, &full[s]);
@@ -272,11 +286,11 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const
       int i = 0;
       for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++i) {
         const int acc = i & 1;
-        mbar_wait(&tmem_empty[acc], (uint32_t)(((i >> 1) & 1) ^ 1));   // the epilogue drained this buffer's last use
+        mbar_wait_bounded(&tmem_empty[acc], (uint32_t)(((i >> 1) & 1) ^ 1));   // the epilogue drained this buffer's last use
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kPBN);
         for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&full[s], ph);
+          mbar_wait_bounded(&full[s], ph);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + s * kPTileA), b_addr = smem_u32(sB + s * kPTileB);
 #pragma unroll
@@ -299,7 +313,7 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const
     for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++i) {
       const int acc = i & 1;
       const int m0 = (t % mt) * kBM, n0 = (t / mt) * kPBN;
-      mbar_wait(&tmem_full[acc], (uint32_t)((i >> 1) & 1));
+      mbar_wait_bounded(&tmem_full[acc], (uint32_t)((i >> 1) & 1));
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
 #pragma unroll 1

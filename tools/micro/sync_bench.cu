@@ -78,7 +78,14 @@ step_kernel(float* vec, unsigned long long* ctr, const unsigned long long* epoch
                                           // advances the epoch, which none of its own CTAs may still have to read)
       if (threadIdx.x == 0) {
         const unsigned long long target = (*epoch + 1ull) * gridDim.x;
+        unsigned int spins = 0;
+        unsigned long long t0 = 0;
         while (ld_acquire(ctr + 16 * (step - 1)) < target) {
+          if ((++spins & 0xfffu) == 0) {
+            const unsigned long long now = gtime();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > 2000000000ull) __trap();
+          }
         }
       }
       __syncthreads();
@@ -105,7 +112,14 @@ persistent_kernel(float* vec, unsigned long long* bar, int steps, int replicas, 
     if (threadIdx.x == 0) {
       target += gridDim.x;
       red_release(bar);
+      unsigned int spins = 0;
+      unsigned long long t0 = 0;
       while (ld_acquire(bar) < target) {
+        if ((++spins & 0xfffu) == 0) {  // never hang the GPU: a CTA that is not co-resident would stall everyone
+          const unsigned long long now = gtime();
+          if (t0 == 0) t0 = now;
+          if (now - t0 > 2000000000ull) __trap();
+        }
       }
     }
     __syncthreads();
