@@ -211,7 +211,7 @@ def reference_cuda_baseline(spec, weights):
         prompt = torch.randint(0, spec.vocab, (PROMPT_LEN,), generator=torch.Generator().manual_seed(0)).tolist()
         with tempfile.TemporaryDirectory() as td:
             models.save_checkpoint(spec, weights, td)
-            _, _, timing = rp.run_reference(spec, td, prompt, 2, time_steps=NEW_TOKENS)
+            _, _, timing = rp.run_reference(spec, td, prompt, 2, time_steps=NEW_TOKENS, timeout=180)
         if not timing:
             return {"unavailable": "ref_cuda_decode printed no timing line"}
         return {"value": timing["tokens_per_s"], "unit": "tokens/s", "us_per_token": timing["us_per_token"],

@@ -35,7 +35,7 @@ REF_BIN = ROOT / "oracle" / "_ref" / "ref_cuda_decode"
 FAMILY = {"llama": "llama", "qwen2": "qwen2", "qwen3": "qwen3", "mistral": "mistral"}
 
 
-def run_reference(spec, ckpt_dir, prompt, n_new, forced=None, time_steps=0):
+def run_reference(spec, ckpt_dir, prompt, n_new, forced=None, time_steps=0, timeout=1200):
     """→ (tokens [n_new] int64, logits [n_new, V] float32, timing dict or None) from the reference CUDA binary."""
     d = Path(ckpt_dir)
     (d / "ids.bin").write_bytes(np.asarray(prompt, dtype=np.int64).tobytes())
@@ -52,7 +52,7 @@ def run_reference(spec, ckpt_dir, prompt, n_new, forced=None, time_steps=0):
         cmd += ["--forced", str(d / "forced.bin")]
     if time_steps:
         cmd += ["--time-steps", str(time_steps)]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=1200)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
     if r.returncode != 0:
         raise RuntimeError(f"ref_cuda_decode failed ({r.returncode}): {r.stderr[-800:]}")
     raw = (d / "ref_out.bin").read_bytes()
