@@ -207,7 +207,7 @@ static int engine_launch_token(b200_engine* e, cudaStream_t st, bool with_head) 
   const bool pf = e->l2pf_bytes > 0;
   for (int l = 0; l < d.layers; ++l) {
     GemvPlan q = e->p_qkv[l];
-    if (pf) gemv_plan_prefetch(&q, e->p_o[l], e->lw[l].o_w, e->l2pf_bytes);
+    if (pf) gemv_plan_prefetch(&q, e->p_o[l], e->l2pf_bytes);
     q.p.trace = tr();
     q.p.fs = fs_next((unsigned int)q.grid);
     if ((rc = gemv_launch(q, st, pdl)) != B200_OK) return rc;
@@ -235,8 +235,8 @@ static int engine_launch_token(b200_engine* e, cudaStream_t st, bool with_head) 
     o.p.trace = tr();
     gu.p.trace = tr();
     if (pf) {
-      gemv_plan_prefetch(&o, e->p_gu[l], e->lw[l].gate_up_w, e->l2pf_bytes);
-      gemv_plan_prefetch(&gu, e->p_down[l], e->lw[l].down_w, e->l2pf_bytes);
+      gemv_plan_prefetch(&o, e->p_gu[l], e->l2pf_bytes);
+      gemv_plan_prefetch(&gu, e->p_down[l], e->l2pf_bytes);
     }
     o.p.fs = fs_next((unsigned int)o.grid);
     if ((rc = gemv_launch(o, st, pdl)) != B200_OK) return rc;
@@ -248,8 +248,8 @@ static int engine_launch_token(b200_engine* e, cudaStream_t st, bool with_head) 
     dn.p.pos_inc = (last_node && !tp) ? e->pos : nullptr;  // the LAST kernel of a token advances the position
     dn.p.trace = tr();
     if (pf) {
-      if (l + 1 < d.layers) gemv_plan_prefetch(&dn, e->p_qkv[l + 1], e->lw[l + 1].qkv_w, e->l2pf_bytes);
-      else if (with_head) gemv_plan_prefetch(&dn, e->p_head, e->head_w, e->l2pf_bytes);
+      if (l + 1 < d.layers) gemv_plan_prefetch(&dn, e->p_qkv[l + 1], e->l2pf_bytes);
+      else if (with_head) gemv_plan_prefetch(&dn, e->p_head, e->l2pf_bytes);
     }
     dn.p.fs = fs_next((unsigned int)dn.grid);
     if (fs && last_node && !tp) {  // full dependency instead of a poll; the only place a body-only token advances the
@@ -262,7 +262,7 @@ static int engine_launch_token(b200_engine* e, cudaStream_t st, bool with_head) 
   if (with_head) {
     GemvPlan hd = e->p_head;
     hd.p.trace = tr();
-    if (pf) gemv_plan_prefetch(&hd, e->p_qkv[0], e->lw[0].qkv_w, e->l2pf_bytes);  // the next token starts there
+    if (pf) gemv_plan_prefetch(&hd, e->p_qkv[0], e->l2pf_bytes);  // the next token starts there
     hd.p.fs = fs_next((unsigned int)hd.grid);
     if ((rc = gemv_launch(hd, st, pdl)) != B200_OK) return rc;
     int64_t* amax = reinterpret_cast<int64_t*>((uint8_t*)e->argmax_ws + argmax_workspace_bytes(1, e->V_l));

@@ -64,7 +64,8 @@ __device__ __forceinline__ void st_volatile_u2(uint2* p, const uint2 v) {
 constexpr int kSmallkMaxRb = 6;
 template <int RPW, int NSEG, int PRO, int EPI, bool FS, bool SMALLK = false>
 __global__ void __launch_bounds__(kThreads, 1)
-gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap) {
+gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap,
+                   const __grid_constant__ CUtensorMap pf_tmap) {
   constexpr int kBoxR = kNW * RPW;
   constexpr int KB = kboxes(RPW, NSEG);                 // 256-column boxes per stage (stage = 16 KB, 32 KB for 4×2)
   constexpr int kBoxBytes = kBoxR * kRowBytes;
@@ -117,15 +118,25 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
           }
         }
       }
-      // cross-kernel L2 prefetch (opt-in, gemv.cuh): queued behind this CTA's own last loads
+      // cross-kernel L2 prefetch (opt-in, gemv.cuh): queued behind this CTA's own last loads.  This CTA covers the
+      // next kernel's CTAs c ≡ blockIdx.x (mod gridDim.x), stage t of CTA c = (row block c + (t / ksteps)·grid, k step
+      // t % ksteps), exactly the boxes that kernel's producer will ask for once its ring slots free up.
+      if (p.pf_count != 0) {
 #pragma unroll 1
-      for (int i = 0; i < 2; ++i) {
-        if (p.pf_bytes[i] != 0) {
-          const char* a = static_cast<const char*>(p.pf_ptr[i]) + (size_t)blockIdx.x * p.pf_bytes[i];
+        for (int c = (int)blockIdx.x; c < p.pf_grid; c += (int)gridDim.x) {
 #pragma unroll 1
-          for (unsigned int off = 0; off < p.pf_bytes[i]; off += 16384u) {
-            const unsigned int n = min(16384u, p.pf_bytes[i] - off);
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a + off), "r"(n) : "memory");
+          for (int t = p.pf_begin; t < p.pf_begin + p.pf_count; ++t) {
+            const int rb = c + (t / p.pf_ksteps) * p.pf_grid;
+            if (rb >= p.pf_rowblocks) break;
+            const int ks = t % p.pf_ksteps;
+#pragma unroll 1
+            for (int kb = 0; kb < p.pf_kb; ++kb)
+#pragma unroll 1
+              for (int seg = 0; seg < p.pf_nseg; ++seg)
+                asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(
+                                 reinterpret_cast<uint64_t>(&pf_tmap)),
+                             "r"((ks * p.pf_kb + kb) * kBoxK), "r"(seg * p.pf_seg_rows + rb * p.pf_box_r)
+                             : "memory");
           }
         }
       }
@@ -497,7 +508,7 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
 }
 
 // ------------------------------------------------------------------------------------------------------ dispatch
-using KernelFn = void (*)(const GemvParams, const CUtensorMap);
+using KernelFn = void (*)(const GemvParams, const CUtensorMap, const CUtensorMap);
 
 // SMALLK instantiations: RPW 1, the single-GPU engine's three k = H launches
 KernelFn pick_smallk(int nseg, int pro, int epi, bool fs) {
@@ -670,28 +681,33 @@ int gemv_make_plan(GemvPlan* plan, const void* W, int64_t rows_total, int64_t n,
   B200_CHECK_ARG(pick(sh.rpw, nseg, pro, epi) != nullptr, "gemv: no kernel for nseg=%d pro=%d epi=%d", nseg, pro, epi);
   B200_CHECK_ARG(plan->smem <= kGemvMaxSmem + 4096, "gemv: k=%lld needs %d bytes of shared memory", (long long)k,
                  plan->smem);
-  return make_tmap_2d_bf16(&plan->tmap, W, rows_total, k, sh.box_r, kBoxK);
+  const int trc = make_tmap_2d_bf16(&plan->tmap, W, rows_total, k, sh.box_r, kBoxK);
+  plan->pf_tmap = plan->tmap;  // a valid descriptor even when nothing is prefetched
+  return trc;
 }
 
-void gemv_plan_prefetch(GemvPlan* cur, const GemvPlan& next, const void* next_W, int64_t budget_bytes) {
-  cur->p.pf_bytes[0] = cur->p.pf_bytes[1] = 0;
-  cur->p.pf_ptr[0] = cur->p.pf_ptr[1] = nullptr;
-  if (budget_bytes <= 0 || next_W == nullptr || cur->grid <= 0) return;
-  const int box_r = 8 * next.rpw;
-  const int ksteps = next.p.k_pad / (kBoxK * kboxes(next.rpw, next.nseg));
-  // row blocks per CTA that next's ring holds completely; row blocks are dealt round-robin, so the rings of all CTAs
-  // together cover a contiguous PREFIX of the rows (of each segment)
-  const int64_t rb_cov = std::max<int64_t>(1, next.p.stages / std::max(1, ksteps));
-  const int64_t start_row = std::min<int64_t>(next.p.n, rb_cov * next.grid * box_r);
-  const int64_t row_bytes = (int64_t)next.p.k * 2;
-  const int64_t rows = std::min<int64_t>(next.p.n - start_row, budget_bytes / next.nseg / row_bytes);
-  if (rows <= 0) return;
-  const int64_t per_cta = (rows * row_bytes / cur->grid) / 128 * 128;   // whole lines; 16-byte aligned by construction
-  if (per_cta <= 0 || per_cta > (1ll << 30)) return;
-  for (int seg = 0; seg < next.nseg; ++seg) {
-    cur->p.pf_ptr[seg] = static_cast<const char*>(next_W) + ((int64_t)seg * next.p.seg_rows + start_row) * row_bytes;
-    cur->p.pf_bytes[seg] = (unsigned int)per_cta;
-  }
+void gemv_plan_prefetch(GemvPlan* cur, const GemvPlan& next, int64_t budget_bytes) {
+  cur->p.pf_count = 0;
+  if (budget_bytes <= 0 || cur->grid <= 0 || next.grid <= 0) return;
+  const int kb = kboxes(next.rpw, next.nseg);
+  const int ksteps = next.p.k_pad / (kBoxK * kb);
+  const int64_t stage_bytes = (int64_t)kb * next.nseg * 8 * next.rpw * kRowBytes;
+  const int64_t rbs_per_cta = (next.p.rowblocks + next.grid - 1) / next.grid;
+  const int64_t total_stages = rbs_per_cta * ksteps;                      // of next's busiest CTA
+  const int64_t begin = next.p.stages;                                    // its ring holds stages [0, stages)
+  int64_t count = budget_bytes / (stage_bytes * next.grid);
+  count = std::min<int64_t>(count, total_stages - begin);
+  if (count <= 0) return;
+  cur->pf_tmap = next.tmap;
+  cur->p.pf_begin = (int)begin;
+  cur->p.pf_count = (int)count;
+  cur->p.pf_grid = next.grid;
+  cur->p.pf_rowblocks = next.p.rowblocks;
+  cur->p.pf_ksteps = ksteps;
+  cur->p.pf_kb = kb;
+  cur->p.pf_nseg = next.nseg;
+  cur->p.pf_box_r = 8 * next.rpw;
+  cur->p.pf_seg_rows = next.p.seg_rows;
 }
 
 int gemv_launch(const GemvPlan& plan, cudaStream_t stream, bool pdl) {
@@ -702,7 +718,8 @@ int gemv_launch(const GemvPlan& plan, cudaStream_t stream, bool pdl) {
     set_error("gemv: no kernel instantiation (nseg=%d pro=%d epi=%d flag-sync=%d)", plan.nseg, plan.pro, plan.epi, (int)fs);
     return B200_ERR_INVALID;
   }
-  B200_CUDA(launch_pdl(f, dim3(plan.grid), dim3(kThreads), (size_t)plan.smem, stream, pdl, plan.p, plan.tmap));
+  B200_CUDA(launch_pdl(f, dim3(plan.grid), dim3(kThreads), (size_t)plan.smem, stream, pdl, plan.p, plan.tmap,
+                       plan.pf_tmap));
   return B200_OK;
 }
 
