@@ -22,6 +22,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
 
 namespace b200 {
 
@@ -401,15 +402,16 @@ int launch_gemm_bf16(void* C, const void* A, const void* B, int64_t M, int64_t N
   int rc;
   const char* mode = std::getenv("B200_GEMM");
   if (mode != nullptr && mode[0] == 'p') {  // "persistent": opt-in, see gemm_tcgen05_persistent_kernel
-    static bool p_attr_set = false;
+    static std::once_flag p_once;
+    static cudaError_t p_err = cudaSuccess;
     static int sms = 0;
-    if (!p_attr_set) {
-      B200_CUDA(cudaFuncSetAttribute(gemm_tcgen05_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPGemmSmem));
+    std::call_once(p_once, [] {
+      p_err = cudaFuncSetAttribute(gemm_tcgen05_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPGemmSmem);
       int dev = 0;
-      B200_CUDA(cudaGetDevice(&dev));
-      B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-      p_attr_set = true;
-    }
+      if (p_err == cudaSuccess) p_err = cudaGetDevice(&dev);
+      if (p_err == cudaSuccess) p_err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    });
+    B200_CUDA(p_err);
     if ((rc = make_tmap_sw128(&ta, A, M, K, kBM)) != B200_OK) return rc;
     if ((rc = make_tmap_sw128(&tb, B, N, K, kPBN)) != B200_OK) return rc;
     const int64_t tiles = ((M + kBM - 1) / kBM) * ((N + kPBN - 1) / kPBN);

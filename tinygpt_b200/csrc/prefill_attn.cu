@@ -17,6 +17,7 @@
 #include "ops.cuh"
 
 #include <cstdlib>
+#include <mutex>
 
 namespace b200 {
 
@@ -258,11 +259,12 @@ __global__ void __launch_bounds__(kPfThreads) attn_prefill_mma_kernel(const Pref
 template <int HD>
 int launch_pf(const PrefillAttnParams& p, int B, cudaStream_t st) {
   constexpr int smem = (kBM + 4 * kBN) * HD * 2;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CUDA(cudaFuncSetAttribute(attn_prefill_mma_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  static std::once_flag once;   // one per instantiation; the reference's server has a worker thread next to main
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(attn_prefill_mma_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  });
+  B200_CUDA(attr_err);
   dim3 grid((unsigned)((p.S + kBM - 1) / kBM), (unsigned)p.Hq, (unsigned)B);
   g_launches.fetch_add(1);
   attn_prefill_mma_kernel<HD><<<grid, kPfThreads, smem, st>>>(p);
