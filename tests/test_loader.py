@@ -147,3 +147,16 @@ def test_config_defaults_follow_the_reference(tmp_path):
     (tmp_path / "config.json").write_text(json.dumps({**base, "model_type": "qwen2", "max_position_embeddings": 77}))
     s = loader.load_model_config(tmp_path)
     assert (s.head_dim, s.qkv_bias, s.max_ctx) == (64, True, 77) and loader.load_model_config(tmp_path, max_ctx=9).max_ctx == 9
+
+
+@pytest.mark.parametrize("staging_bytes", [256, 3000, 1 << 16])
+def test_chunked_staging_path(tmp_path, staging_bytes):
+    """The staging-buffer path CUDA destinations use (chunks of rows, strided column slices, rows larger than the
+    buffer) — forced onto a CPU destination with tiny buffers so that every branch runs without a GPU."""
+    spec = models.TINY_LLAMA
+    w = models.synth_weights(spec, seed=11)
+    models.save_checkpoint(spec, w, str(tmp_path))
+    _, got, _ = loader.load_checkpoint(tmp_path, device="cpu", staging_bytes=staging_bytes)
+    _same(got, w)
+    _, r1, _ = loader.load_checkpoint(tmp_path, device="cpu", rank=1, world=2, staging_bytes=staging_bytes)
+    _same(r1, tp.shard_weights(spec, w, 1, 2))

@@ -173,39 +173,59 @@ class _Checkpoint:
 
 class _Copier:
     """uint16 numpy slice → bf16 destination slice; CUDA destinations go through one reusable pinned staging buffer so
-    the H2D copies are asynchronous DMA from page-locked memory instead of a pageable memcpy per tensor."""
+    the H2D copies are asynchronous DMA from page-locked memory instead of a pageable memcpy per tensor.
+    `staging_bytes` on a CPU destination forces the same chunked path through an ordinary buffer (tests)."""
 
-    def __init__(self, device: torch.device, staging_bytes: int = 64 << 20):
+    def __init__(self, device: torch.device, staging_bytes: Optional[int] = None):
         self.device = device
         self.cuda = device.type == "cuda"
-        self.staging = torch.empty(staging_bytes // 2, dtype=torch.int16).pin_memory() if self.cuda else None
+        self.staging = None
+        if self.cuda:
+            self.staging = torch.empty((staging_bytes or (64 << 20)) // 2, dtype=torch.int16).pin_memory()
+        elif staging_bytes:
+            self.staging = torch.empty(staging_bytes // 2, dtype=torch.int16)
         self.bytes = 0
+
+    def _sync(self) -> None:
+        if self.cuda:
+            torch.cuda.current_stream(self.device).synchronize()
 
     def copy(self, dst: torch.Tensor, src: np.ndarray) -> None:
         """dst: contiguous bf16 view with src's shape (a dim-0 range of the destination tensor)."""
         assert tuple(dst.shape) == tuple(src.shape) and dst.is_contiguous()
         self.bytes += src.size * 2
         d16 = dst.view(torch.int16).view(-1)
-        if not self.cuda:
+        if self.staging is None:
             d16.copy_(torch.from_numpy(np.array(src, dtype=np.uint16, copy=True).view(np.int16).reshape(-1)))
             return
         rows = src.shape[0] if src.ndim > 1 else 1
         row_elems = src.size // max(rows, 1)
-        cap_rows = max(1, self.staging.numel() // max(row_elems, 1))
         s2 = src.reshape(rows, row_elems) if src.ndim != 2 else src
+        cap = self.staging.numel()
+        if row_elems > cap:                       # a single row larger than the buffer: walk it in column pieces
+            for r in range(rows):
+                for c0 in range(0, row_elems, cap):
+                    c1 = min(row_elems, c0 + cap)
+                    self._sync()                  # the previous piece has left the staging buffer
+                    np.copyto(self.staging[:c1 - c0].numpy().view(np.uint16), s2[r, c0:c1])
+                    d16[r * row_elems + c0:r * row_elems + c1].copy_(self.staging[:c1 - c0], non_blocking=True)
+            self._sync()
+            return
+        cap_rows = cap // row_elems
         for r0 in range(0, rows, cap_rows):
             r1 = min(rows, r0 + cap_rows)
             n = (r1 - r0) * row_elems
-            torch.cuda.current_stream(self.device).synchronize()      # the previous chunk has left the staging buffer
+            self._sync()                          # the previous chunk has left the staging buffer
             stage = self.staging[:n].numpy().view(np.uint16).reshape(r1 - r0, row_elems)
-            np.copyto(stage, s2[r0:r1])                                 # the only host-side pass: strided or not
+            np.copyto(stage, s2[r0:r1])           # the only host-side pass: strided (column slice) or not
             d16[r0 * row_elems:r0 * row_elems + n].copy_(self.staging[:n], non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
+        self._sync()
 
 
 def load_checkpoint(model_dir: str | Path, device: str | torch.device = "cuda", rank: int = 0, world: int = 1,
                     shard_attn: Optional[bool] = None, max_ctx: Optional[int] = None,
-                    strict_unexpected: bool = False) -> Tuple[models.ModelSpec, Dict[str, torch.Tensor], dict]:
+                    strict_unexpected: bool = False,
+                    staging_bytes: Optional[int] = None) -> Tuple[models.ModelSpec, Dict[str, torch.Tensor], dict]:
     """→ (spec, weights in the engine's merged layout holding rank `rank`'s shards on `device`, report).
 
     The dict plugs straight into DecodeEngine (world == 1) or is what TPDecodeEngine would cut for itself
@@ -227,7 +247,7 @@ def load_checkpoint(model_dir: str | Path, device: str | torch.device = "cuda", 
     else:
         shard_attn = False
     ck = _Checkpoint(model_dir)
-    cp = _Copier(dev)
+    cp = _Copier(dev, staging_bytes)
     H, qd, kvd, I, V = spec.hidden, spec.q_dim, spec.kv_dim, spec.intermediate, spec.vocab
     qd_l, kvd_l = (qd // world, kvd // world) if shard_attn else (qd, kvd)
     a_rank = rank if shard_attn else 0                  # attention slices (replicated ⇒ everything from offset 0)
