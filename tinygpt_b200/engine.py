@@ -208,15 +208,13 @@ class DecodeEngine:
         if prompt.numel() == 0:
             raise B200Error("generate_async: empty prompt")
         S = prompt.shape[1]
-        ids_dev = prompt.pin_memory().to(self.device, non_blocking=True)
         self.reset_cache()
-        base = int(lib().b200_engine_generated(self._h))      # tokens generated before this call
-        stream = self._stream()
-        check(lib().b200_engine_forward(self._h, ids_dev.data_ptr(), 1, S, None, 0, stream), "b200_engine_forward")
+        base = self._generated()                               # tokens generated before this call
+        self._enqueue_prefill(prompt)
         launched, out, reason = 1, [], "length"
         while len(out) < max_new_tokens:
             while launched < max_new_tokens and launched - len(out) < lookahead:
-                check(lib().b200_engine_decode(self._h, 1, None, stream), "b200_engine_decode")
+                self._enqueue_step()
                 launched += 1
             tok = self._fetch_token(base + len(out) + 1)
             if tok in eos:
@@ -226,10 +224,25 @@ class DecodeEngine:
             if callback is not None and not callback(tok):
                 reason = "stop"
                 break
-        torch.cuda.current_stream(self.device).synchronize()
+        self._drain()
         # position of the next input token = S + (tokens kept) - 1 … the last kept token has not been fed yet unless a
         # look-ahead step consumed it; rewinding there makes both cases equal
         keep = max(len(out), 1)
         if S + keep - 1 < self.position:
             self.seek(S + keep - 1)
         return out, reason
+
+    # the four touch points of generate_async with the device (overridden by the host-logic test's fake engine)
+    def _generated(self) -> int:
+        return int(lib().b200_engine_generated(self._h))
+
+    def _enqueue_prefill(self, prompt: torch.Tensor) -> None:
+        ids_dev = prompt.pin_memory().to(self.device, non_blocking=True)
+        check(lib().b200_engine_forward(self._h, ids_dev.data_ptr(), 1, prompt.shape[1], None, 0, self._stream()),
+              "b200_engine_forward")
+
+    def _enqueue_step(self) -> None:
+        check(lib().b200_engine_decode(self._h, 1, None, self._stream()), "b200_engine_decode")
+
+    def _drain(self) -> None:
+        torch.cuda.current_stream(self.device).synchronize()
