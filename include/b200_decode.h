@@ -29,7 +29,8 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden; these are its only exports */
 #endif
 
-#define B200_ABI_VERSION 1
+/* 2: + b200_engine_set_mailbox, b200_engine_generated (additive; version-1 callers keep working) */
+#define B200_ABI_VERSION 2
 
 typedef enum b200_status {
   B200_OK = 0,

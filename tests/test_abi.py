@@ -95,3 +95,12 @@ def test_rope_table_host_equals_oracle():
         cfg = to_oracle_cfg(spec)
         assert torch.equal(models.rope_table(spec), orc.rope_table(spec.head_dim, spec.max_ctx, spec.rope_theta,
                                                                    cfg.rope_scaling))
+
+
+def test_header_is_plain_c_and_cxx():
+    """The boundary is a C ABI: the header must compile as C99 (pedantic) and as C++17 on its own."""
+    hdr = str(ROOT / "include" / "b200_decode.h")
+    for cmd in (["gcc", "-x", "c", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", hdr],
+                ["g++", "-x", "c++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", hdr]):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
