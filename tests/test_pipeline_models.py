@@ -239,3 +239,32 @@ def test_flagsync_counter_protocol():
         rng = random.Random(seed)
         kinds = [rng.choice(["step", "body"]) for _ in range(7)]
         run_flagsync(kinds, nlayer_ops=10, ctas_per_op=[5, 3, 4, 6, 2], rng=rng)
+
+
+# ------------------------------------------------------------------------------ persistent GEMM: tile walk + epilogue cover
+@pytest.mark.parametrize("M,N,sms", [(128, 256, 148), (1, 128, 148), (130, 136, 148), (200, 896, 148), (16, 1152, 148),
+                                     (2048, 4096, 148), (384, 40000, 148), (512, 12288, 7)])
+def test_persistent_gemm_writes_every_element_once(M, N, sms):
+    """gemm.cu gemm_tcgen05_persistent_kernel: tiles t = blockIdx.x + i·gridDim.x, m-fastest (m0 = (t % mt)·128,
+    n0 = (t / mt)·256); epilogue warp quarter q / lane own row m0 + 32q + lane and walk 256 columns in 16-wide pieces,
+    guarded by row < M and n0 + c < N (+ per-element guard in the ragged piece)."""
+    import numpy as np
+    BM, BN = 128, 256
+    mt, nt = (M + BM - 1) // BM, (N + BN - 1) // BN
+    tiles = mt * nt
+    grid = min(tiles, sms)
+    hits = np.zeros((M, N), dtype=np.int32)
+    acc_use = {}
+    for b in range(grid):
+        i = 0
+        for t in range(b, tiles, grid):
+            m0, n0 = (t % mt) * BM, (t // mt) * BN
+            acc_use.setdefault(b, []).append(i & 1)
+            rows = np.arange(m0, m0 + BM)
+            rows = rows[rows < M]
+            for c in range(0, BN, 16):
+                if n0 + c < N:
+                    hits[np.ix_(rows, np.arange(n0 + c, min(N, n0 + c + 16)))] += 1
+            i += 1
+    assert (hits == 1).all()
+    assert all(u == [k & 1 for k in range(len(u))] for u in acc_use.values())   # accumulator buffers strictly alternate
