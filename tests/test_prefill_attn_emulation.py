@@ -1,8 +1,10 @@
 """CPU emulation of csrc/prefill_attn.cu's data movement: the XOR-swizzled shared-memory tiles, the per-lane ldmatrix
 addresses, the mma.sync m16n8k16 fragment layouts, the S→P register re-use, the causal mask indices and the
 double-buffered tile loop — lane by lane, following the kernel statement by statement — checked against the oracle's
-flash attention.  It cannot prove the PTX semantics (those are restated here from the PTX ISA's fragment figures), but
-it pins every index formula of the kernel without a GPU.  The GPU run of the real kernel is tests/test_staged_gpu.py.
+flash attention.  It cannot prove the PTX semantics (those are restated here from the PTX ISA's fragment figures; the
+A/B/C fragment maps used by mma_16816() below were cross-checked against CUTLASS' own statement of them,
+cute/atom/mma_traits_sm80.hpp MMA_Traits<SM80_16x8x16_F32BF16BF16F32_TN>: ALayout/BLayout/SM80_16x8_Row), but it pins
+every index formula of the kernel without a GPU.  The GPU run of the real kernel is tests/test_staged_gpu.py.
 """
 import math
 
