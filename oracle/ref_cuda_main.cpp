@@ -6,7 +6,12 @@
 //
 //   ref_cuda_decode --ckpt DIR --family {llama|qwen2|qwen3|mistral} --dims H,L,Hq,Hkv,hd,I,V,ctx --theta T --eps E
 //                   --tie {0|1} [--rope-scaling f,hi,lo,orig] --ids FILE(int64) --new N [--forced FILE(int64)]
-//                   --out FILE [--time-steps K]
+//                   --out FILE [--time-steps K] [--b200 {off|ops|engine}] [--qkv-bias 0|1] [--qk-norm 0|1]
+// --b200 exercises the DROP-IN BOUNDARY with the real reference code around it (integration/tinytorch_b200_adapter.h,
+// linked against tinygpt_b200/lib/libb200decode.so):  ops    = b200::adapter::registerOps() — boundary B, the
+// reference's modules call our kernels through its own op registry;  engine = the loaded GPTModel wrapped in
+// b200::adapter::ModelB200 — boundary A, GPTModel::forward → virtual model() → b200_engine_forward.  Everything else
+// (loader, tensors, generate loop, argmax) stays the reference's.
 // Output file: int64 N tokens, then float32 [N, V] logits (last position of the prefill, then every decode step).
 // With --forced the decode steps consume the given tokens (teacher forcing) instead of the reference's own argmax.
 // The loop is GPTEngine::generateSync's (src/engine/GPTEngine.cpp:154-174): genNextToken = forward → narrow last →
@@ -30,6 +35,7 @@
 #include "model/ModelMistral.h"
 #include "model/ModelQwen2.h"
 #include "model/ModelQwen3.h"
+#include "tinytorch_b200_adapter.h"
 
 namespace tt = tinytorch;
 namespace hf = tinygpt::huggingface::model;
@@ -78,7 +84,8 @@ int main(int argc, char** argv) {
   std::string ckpt, family, idsPath, forcedPath, outPath;
   std::vector<double> dims, rs;
   float theta = 10000.f, eps = 1e-5f;
-  int tie = 1, nNew = 8, timeSteps = 0;
+  int tie = 1, nNew = 8, timeSteps = 0, qkvBias = -1, qkNorm = -1;
+  std::string b200Mode = "off";
   for (int i = 1; i + 1 < argc; i += 2) {
     const std::string a = argv[i];
     const char* v = argv[i + 1];
@@ -94,6 +101,9 @@ int main(int argc, char** argv) {
     else if (a == "--new") nNew = atoi(v);
     else if (a == "--out") outPath = v;
     else if (a == "--time-steps") timeSteps = atoi(v);
+    else if (a == "--b200") b200Mode = v;
+    else if (a == "--qkv-bias") qkvBias = atoi(v);
+    else if (a == "--qk-norm") qkNorm = atoi(v);
   }
   if (ckpt.empty() || dims.size() != 8 || idsPath.empty() || outPath.empty()) {
     fprintf(stderr, "usage: see the header of oracle/ref_cuda_main.cpp\n");
@@ -139,6 +149,29 @@ int main(int argc, char** argv) {
   }
   model->model().to(tt::DType::BFloat16);
   model->model().eval();
+  if (b200Mode == "ops") {
+    b200::adapter::registerOps();           // from main(), after static initialisation
+  } else if (b200Mode == "engine") {
+    b200_model_desc d{};
+    d.hidden = (int32_t)dims[0];
+    d.layers = (int32_t)dims[1];
+    d.q_heads = (int32_t)dims[2];
+    d.kv_heads = (int32_t)dims[3];
+    d.head_dim = (int32_t)dims[4];
+    d.intermediate = (int32_t)dims[5];
+    d.vocab = (int32_t)dims[6];
+    d.max_ctx = (int32_t)dims[7];
+    d.rms_eps = eps;
+    d.qkv_bias = qkvBias >= 0 ? qkvBias : (family == "qwen2");
+    d.qk_norm = qkNorm >= 0 ? qkNorm : (family == "qwen3");
+    d.tp_rank = 0;
+    d.tp_world = 1;
+    d.tp_shard_attn = 1;
+    model = std::make_unique<b200::adapter::ModelB200>(std::move(model), d);
+  } else if (b200Mode != "off") {
+    fprintf(stderr, "--b200 must be off, ops or engine\n");
+    return 2;
+  }
 
   const std::vector<int64_t> ids = readI64(idsPath);
   const std::vector<int64_t> forced = forcedPath.empty() ? std::vector<int64_t>() : readI64(forcedPath);
@@ -191,8 +224,9 @@ int main(int argc, char** argv) {
     }
     cudaDeviceSynchronize();
     const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    printf("{\"impl\": \"reference-cuda\", \"tokens_per_s\": %.3f, \"us_per_token\": %.2f, \"steps\": %d, \"prompt\": %lld}\n",
-           timeSteps / dt, dt / timeSteps * 1e6, timeSteps, (long long)S);
+    printf("{\"impl\": \"reference-cuda\", \"b200\": \"%s\", \"tokens_per_s\": %.3f, \"us_per_token\": %.2f, \"steps\": %d, "
+           "\"prompt\": %lld}\n",
+           b200Mode.c_str(), timeSteps / dt, dt / timeSteps * 1e6, timeSteps, (long long)S);
   }
   fflush(stdout);
   _exit(0);  // skip static destructors (the reference's allocator asserts on teardown order)

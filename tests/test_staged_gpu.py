@@ -403,3 +403,33 @@ def test_engine_and_oracle_against_reference_cuda(built_lib):
         srt = torch.sort(ref_logits, dim=-1, descending=True).values
         decided = (srt[:, 0] - srt[:, 1]) > 4 * ulp
         assert torch.equal(ref_toks[decided], toks[decided]), f"{spec.name}: greedy ids differ on decisive steps"
+
+
+def test_drop_in_boundary_inside_the_real_reference(built_lib):
+    """The SAME reference program (its loader, modules, KV manager, generate loop, argmax) with
+    (a) our engine behind GPTModel::model() via b200::adapter::ModelB200 — must reproduce our Python-driven engine bit
+        for bit (same library, same weights, same prefill path), and
+    (b) our kernels behind its op registry via b200::adapter::registerOps() — must stay within the summation-order floor
+        of the plain reference."""
+    import sys
+    import tempfile
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tools"))
+    import ref_cuda_parity as rp
+    if not rp.REF_BIN.exists():
+        pytest.skip("oracle/_ref/ref_cuda_decode not built (needs /root/reference: make -C oracle cuda)")
+    for spec in (models.TINY_QWEN2, models.TINY_QWEN3, models.TINY_MISTRAL):
+        w = models.synth_weights(spec, seed=0)
+        prompt = torch.randint(0, spec.vocab, (16,), generator=torch.Generator().manual_seed(0)).tolist()
+        with tempfile.TemporaryDirectory() as td:
+            models.save_checkpoint(spec, w, td)
+            toks, logits, _ = rp.run_engine(spec, w, prompt, 12)
+            _, ref_logits, _ = rp.run_reference(spec, td, prompt, 12, forced=toks.tolist())
+            t_eng, l_eng, _ = rp.run_reference(spec, td, prompt, 12, forced=toks.tolist(), b200="engine")
+            t_ops, l_ops, _ = rp.run_reference(spec, td, prompt, 12, forced=toks.tolist(), b200="ops")
+        assert torch.equal(l_eng, logits) and torch.equal(t_eng, toks), f"{spec.name}: adapter engine != Python engine"
+        top = float(ref_logits.abs().max())
+        ulp = 2.0 ** (torch.floor(torch.log2(torch.tensor(top))).item() - 7)
+        d = (l_ops - ref_logits).abs()
+        print(f"[{spec.name}] reference + our ops vs plain reference: mean {float(d.mean()):.3e} max {float(d.max()):.3e}")
+        assert float(d.mean()) <= 4e-3 and float(d.max()) <= 8 * ulp

@@ -35,15 +35,18 @@ REF_BIN = ROOT / "oracle" / "_ref" / "ref_cuda_decode"
 FAMILY = {"llama": "llama", "qwen2": "qwen2", "qwen3": "qwen3", "mistral": "mistral"}
 
 
-def run_reference(spec, ckpt_dir, prompt, n_new, forced=None, time_steps=0, timeout=1200):
-    """→ (tokens [n_new] int64, logits [n_new, V] float32, timing dict or None) from the reference CUDA binary."""
+def run_reference(spec, ckpt_dir, prompt, n_new, forced=None, time_steps=0, timeout=1200, b200="off"):
+    """→ (tokens [n_new] int64, logits [n_new, V] float32, timing dict or None) from the reference CUDA binary.
+    b200 = "ops" / "engine": the same reference program with our kernels behind its op registry (boundary B) / our
+    engine behind GPTModel::model() (boundary A), through integration/tinytorch_b200_adapter.h."""
     d = Path(ckpt_dir)
     (d / "ids.bin").write_bytes(np.asarray(prompt, dtype=np.int64).tobytes())
     cmd = [str(REF_BIN), "--ckpt", str(d), "--family", FAMILY[spec.model_type], "--dims",
            ",".join(str(int(v)) for v in (spec.hidden, spec.layers, spec.q_heads, spec.kv_heads, spec.head_dim,
                                           spec.intermediate, spec.vocab, spec.max_ctx)),
            "--theta", repr(float(spec.rope_theta)), "--eps", repr(float(spec.rms_eps)), "--tie", str(int(spec.tie)),
-           "--ids", str(d / "ids.bin"), "--new", str(n_new), "--out", str(d / "ref_out.bin")]
+           "--ids", str(d / "ids.bin"), "--new", str(n_new), "--out", str(d / "ref_out.bin"), "--b200", b200,
+           "--qkv-bias", str(int(spec.qkv_bias)), "--qk-norm", str(int(spec.qk_norm))]
     if spec.rope_scaling is not None:
         sc = spec.rope_scaling
         cmd += ["--rope-scaling", f"{sc.factor},{sc.high_freq_factor},{sc.low_freq_factor},{sc.original_context_length}"]
@@ -137,6 +140,20 @@ def main():
             row["oracle_vs_reference_cuda"] = compare("oracle-ref", logits_orc, ref_logits)
             row["engine_vs_oracle"] = compare("engine-oracle", logits, logits_orc)
         row["decode_us_per_token"] = {"ours": us, "reference_cuda": timing["us_per_token"] if timing else None}
+        # the drop-in boundary with the real reference around it: same program, our code behind its seams
+        with tempfile.TemporaryDirectory() as td:
+            models.save_checkpoint(spec, w, td)
+            for mode in ("ops", "engine"):
+                try:
+                    t_m, l_m, tim = run_reference(spec, td, prompt, args.new, forced=toks.tolist(), b200=mode,
+                                                  time_steps=128 if big else 32)
+                    row[f"reference_with_b200_{mode}"] = {
+                        "vs_plain_reference": compare(f"{mode}-ref", l_m, ref_logits),
+                        "vs_our_python_engine": compare(f"{mode}-engine", l_m, logits),
+                        "greedy_ids_equal_to_ours": int((t_m == toks).sum()), "steps": int(len(toks)),
+                        "us_per_token_through_the_reference_loop": tim["us_per_token"] if tim else None}
+                except Exception as e:  # noqa: BLE001
+                    row[f"reference_with_b200_{mode}"] = {"failed": str(e)[:400]}
         report.append(row)
         print(json.dumps(row), flush=True)
     if args.json:
