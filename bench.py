@@ -212,11 +212,21 @@ def reference_cuda_baseline(spec, weights):
         with tempfile.TemporaryDirectory() as td:
             models.save_checkpoint(spec, weights, td)
             _, _, timing = rp.run_reference(spec, td, prompt, 2, time_steps=NEW_TOKENS, timeout=180)
+            try:  # the same reference program with our engine behind GPTModel::model() (the TinyTorch adapter)
+                _, _, t_adapter = rp.run_reference(spec, td, prompt, 2, time_steps=NEW_TOKENS, timeout=180, b200="engine")
+            except Exception as e:  # noqa: BLE001
+                t_adapter = {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
         if not timing:
             return {"unavailable": "ref_cuda_decode printed no timing line"}
-        return {"value": timing["tokens_per_s"], "unit": "tokens/s", "us_per_token": timing["us_per_token"],
-                "kind": "reference CUDA build (unmodified sources, oracle/_ref/ref_cuda_decode), same GPU",
-                "sample": f"{NEW_TOKENS} greedy decode steps after a {PROMPT_LEN}-token prompt, device-resident token loop"}
+        out = {"value": timing["tokens_per_s"], "unit": "tokens/s", "us_per_token": timing["us_per_token"],
+               "kind": "reference CUDA build (unmodified sources, oracle/_ref/ref_cuda_decode), same GPU",
+               "sample": f"{NEW_TOKENS} greedy decode steps after a {PROMPT_LEN}-token prompt, device-resident token loop"}
+        if t_adapter:
+            out["same_program_with_b200_engine"] = (
+                {"value": t_adapter["tokens_per_s"], "unit": "tokens/s", "us_per_token": t_adapter["us_per_token"],
+                 "what": "the reference's own generate loop, our engine behind GPTModel::model() via "
+                         "integration/tinytorch_b200_adapter.h"} if "tokens_per_s" in t_adapter else t_adapter)
+        return out
     except Exception as e:  # noqa: BLE001 — a baseline must never take the bench line down
         return {"unavailable": f"{type(e).__name__}: {str(e)[:300]}"}
 
