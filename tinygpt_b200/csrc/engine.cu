@@ -78,7 +78,6 @@ struct b200_engine {
   unsigned long long* mailbox = nullptr;
   unsigned long long mailbox_cap = 1;
   int64_t l2pf_bytes = 0;  // opt-in (B200_L2PF_MB): cross-kernel L2 prefetch budget per GEMV launch (gemv.cuh)
-  const void* head_w = nullptr;
   bool use_flagsync = false;
   unsigned long long* fs_ctr = nullptr;
   unsigned long long* fs_epoch = nullptr;
@@ -424,7 +423,6 @@ static int engine_build(const b200_model_desc* desc, const b200_weight_table* w,
   e->use_flagsync = (env && env[0] == '1') && e->use_pdl && (world == 1 || (env_tp && env_tp[0] == '1'));
   env = std::getenv("B200_L2PF_MB");
   if (env) e->l2pf_bytes = (int64_t)std::max(0, std::min(64, std::atoi(env))) << 20;
-  e->head_w = w->lm_head;
   env = std::getenv("B200_NO_PREFILL_GEMM");
   e->use_prefill_gemm = !(env && env[0] == '1');
   e->final_norm_w = w->final_norm;
