@@ -108,6 +108,7 @@ def main():
     ap.add_argument("--new", type=int, default=24)
     ap.add_argument("--prompt", type=int, default=16)
     ap.add_argument("--json", default="")
+    ap.add_argument("--prefill", default="", help="MODEL:TOKENS, e.g. Qwen3-1.7B:2048 — time the prefill of both paths")
     args = ap.parse_args()
     if not REF_BIN.exists():
         raise SystemExit(f"{REF_BIN} is missing: build it in the container that has /root/reference (make -C oracle cuda)")
@@ -154,6 +155,35 @@ def main():
                         "us_per_token_through_the_reference_loop": tim["us_per_token"] if tim else None}
                 except Exception as e:  # noqa: BLE001
                     row[f"reference_with_b200_{mode}"] = {"failed": str(e)[:400]}
+        report.append(row)
+        print(json.dumps(row), flush=True)
+    # config 4 of BASELINE.json: prefill of a long prompt, the reference's own path vs ours (timing only)
+    if args.prefill:
+        name, plen = args.prefill.split(":")
+        plen = int(plen)
+        spec = models.SPECS[name].with_ctx(plen + 64)
+        w = models.synth_weights(spec, seed=0, device="cuda", device_generator=True)
+        prompt = torch.randint(0, spec.vocab, (plen,), generator=torch.Generator().manual_seed(0)).tolist()
+        row = {"model": name, "prefill_tokens": plen}
+        eng = engine.DecodeEngine(spec, w)
+        p = torch.tensor(prompt, dtype=torch.int64).view(1, -1).cuda()
+        for _ in range(2):
+            eng.reset_cache()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            eng.gen_next_token(p)
+            e1.record()
+            torch.cuda.synchronize()
+        row["ours_prefill_ms"] = e0.elapsed_time(e1)
+        eng.close()
+        with tempfile.TemporaryDirectory() as td:
+            models.save_checkpoint(spec, w, td)
+            try:
+                _, _, tim = run_reference(spec, td, prompt, 2, time_steps=16)
+                row["reference_cuda_prefill_ms"] = tim.get("prefill_ms") if tim else None
+                row["reference_cuda_decode_us_per_token_at_this_ctx"] = tim.get("us_per_token") if tim else None
+            except Exception as e:  # noqa: BLE001
+                row["reference_cuda"] = {"failed": str(e)[:400]}
         report.append(row)
         print(json.dumps(row), flush=True)
     if args.json:
