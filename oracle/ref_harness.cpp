@@ -21,6 +21,7 @@
 #include "model/ModelMistral.h"
 #include "model/ModelQwen2.h"
 #include "model/ModelQwen3.h"
+#include "engine/Sampler.h"
 
 namespace tt = tinytorch;
 
@@ -135,6 +136,54 @@ void ref_argmax_f32(const float* x, int64_t rows, int64_t V, int64_t* out) {
   tt::NoGradGuard g;
   auto idx = tt::function::argmax(fromF32(x, {rows, V}), -1, true);
   std::memcpy(out, idx.dataPtr<int64_t>(), sizeof(int64_t) * rows);
+}
+
+// ---- sampler: the reference's own Sampler::sample (src/engine/Sampler.cpp, compiled unmodified) with ONE hook: the
+// CPU `multinomial` op is replaced, through the reference's registry, by a shim that records the probability vector
+// the sampler hands it and draws by inverse CDF from a caller-supplied uniform number — so the filtering pipeline
+// (temperature, top-k, top-p, min-p) that runs is the reference's, and the draw is reproducible.
+static std::vector<float>* g_capturedProbs = nullptr;
+static float g_uniform = 0.f;
+
+static tt::Tensor multinomialShim(const tt::Tensor& probs, int64_t nSamples, bool /*replacement*/) {
+  ASSERT(nSamples == 1 && probs.dim() == 2 && probs.shape(0) == 1);
+  const int64_t n = probs.shape(1);
+  tt::Tensor f = probs.dtype() == tt::DType::Float32 ? probs : probs.to(tt::DType::Float32);
+  const float* p = f.dataPtr<float>();
+  if (g_capturedProbs) g_capturedProbs->assign(p, p + n);
+  // kMultinomialWithReplacement's rule (third_party/TinyTorch/src/Operation/OpSamplingCuda.cu:37-62): inclusive fp32
+  // cumulative sum in index order, r = u * total, first index whose cdf >= r
+  float total = 0.f;
+  for (int64_t i = 0; i < n; i++) total += p[i];
+  const float r = g_uniform * total;
+  float c = 0.f;
+  int64_t pick = 0;
+  for (int64_t i = 0; i < n; i++) {
+    c += p[i];
+    if (c >= r) {
+      pick = i;
+      break;
+    }
+  }
+  tt::Tensor out = tt::Tensor::empty({1, 1}, tt::Options(tt::Device(tt::DeviceType::CPU), tt::DType::Int64));
+  out.dataPtr<int64_t>()[0] = pick;
+  return out;
+}
+
+// logits [V] fp32 → probabilities after the reference's filtering [V] fp32, and the index drawn with uniform u.
+int64_t ref_sampler_f32(const float* logits, int64_t V, float temperature, int64_t topK, float topP, float minP,
+                        float u, float* probs_out) {
+  tt::NoGradGuard g;
+  tt::op::multinomialRegistry::registerImpl({tt::DeviceType::CPU, tt::DType::Float32}, &multinomialShim);
+  std::vector<float> captured;
+  g_capturedProbs = &captured;
+  g_uniform = u;
+  tinygpt::Sampler sampler(tinygpt::SamplerConfig(temperature, topK, topP, minP));
+  tt::Tensor idx = sampler.sample(fromF32(logits, {1, V}));
+  g_capturedProbs = nullptr;
+  if (probs_out && (int64_t)captured.size() == V) std::memcpy(probs_out, captured.data(), sizeof(float) * V);
+  if (captured.empty() && probs_out) std::memset(probs_out, 0, sizeof(float) * V);  // greedy branch: no multinomial
+  return idx.to(tt::DType::Int64).dataPtr<int64_t>()[0];
 }
 
 // ---- whole model ---------------------------------------------------------------------------------------------

@@ -140,5 +140,33 @@ for spec in (models.TINY_QWEN2, models.TINY_LLAMA, models.TINY_QWEN3, models.TIN
     print(spec.name, "states", n, "logits std", float(logits.std()))
 np.savez_compressed(ROOT / "tests" / "golden" / "ref_cpu_models.npz", **out)
 print("wrote fixtures")
+
+
+# ---------------------------------------------------------------------------------------------------- sampler
+# The reference's own Sampler::sample (src/engine/Sampler.cpp, compiled unmodified into the library) with the CPU
+# `multinomial` op hooked through the registry (oracle/ref_harness.cpp ref_sampler_f32): records the probabilities the
+# sampler hands to multinomial and draws by inverse CDF from a given uniform number.
+lib.ref_sampler_f32.restype = C.c_int64
+lib.ref_sampler_f32.argtypes = [F, C.c_int64, C.c_float, C.c_int64, C.c_float, C.c_float, C.c_float, F]
+srng = np.random.default_rng(4321)
+SAMPLER_CFGS = [(0.8, 0, 1.0, 0.0), (1.0, 50, 1.0, 0.0), (0.7, 0, 0.9, 0.0), (1.3, 0, 1.0, 0.05), (0.6, 40, 0.95, 0.02),
+                (2.0, 5, 0.5, 0.0), (1.0, 1, 1.0, 0.0), (0.9, 0, 0.0001, 0.0), (1.0, 100000, 0.999, 0.5),
+                (0.0, 0, 1.0, 0.0)]
+SAMPLER_U = [0.0001, 0.37, 0.62, 0.9999]
+samp = {"cfgs": np.array(SAMPLER_CFGS, dtype=np.float64), "u": np.array(SAMPLER_U, dtype=np.float32)}
+for V in (97, 2048):
+    logits = (srng.standard_normal(V) * 3).astype(np.float32)
+    samp[f"logits_{V}"] = logits
+    probs = np.zeros((len(SAMPLER_CFGS), V), dtype=np.float32)
+    picks = np.zeros((len(SAMPLER_CFGS), len(SAMPLER_U)), dtype=np.int64)
+    for ci, (T, k, tp_, mp) in enumerate(SAMPLER_CFGS):
+        for ui, u in enumerate(SAMPLER_U):
+            out = np.zeros(V, dtype=np.float32)
+            picks[ci, ui] = lib.ref_sampler_f32(fp(logits), V, T, k, tp_, mp, u, fp(out))
+            probs[ci] = out
+    samp[f"probs_{V}"] = probs
+    samp[f"picks_{V}"] = picks
+np.savez_compressed(ROOT / "tests" / "golden" / "ref_cpu_sampler.npz", **samp)
+print("wrote ref_cpu_sampler.npz")
 import os
 os._exit(0)  # skip the reference's static teardown (allocator asserts on destruction order)
