@@ -142,6 +142,15 @@ int b200_attn_decode_bf16(void* out, const void* qkv, const void* q_norm_or_null
                           void* kcache, void* vcache, int64_t Hq, int64_t Hkv, int64_t hd, int64_t max_ctx,
                           void* workspace, void* stream);
 
+/* Sampler::sample for one row of bf16 logits [V] on the device (temperature → top-k → top-p → min-p → softmax →
+ * inverse-CDF draw with the caller's uniform number u in (0, 1]), without sorting the vocabulary (sampling.cu).
+ * [ref: src/engine/Sampler.cpp:31-78; third_party/TinyTorch/src/Operation/OpSamplingCuda.cu:30-62,97-170,261-330]
+ * Greedy decoding (temperature 0, top_k 0, top_p 1, min_p 0) is b200_argmax_bf16.  `workspace`: 256-byte aligned,
+ * b200_sample_workspace_bytes() bytes.  Staged: modelled on the CPU, not yet run on hardware. */
+int64_t b200_sample_workspace_bytes(void);
+int b200_sample_bf16(int64_t* token_out, const void* logits, int64_t V, float temperature, int64_t top_k, float top_p,
+                     float min_p, float u, void* workspace, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Boundary A — the whole per-token forward behind GPTModel::forward / GPTEngine::genNextToken.
  * [ref: src/model/GPTModel.h:51-58 CausalLM::forward, :80-106 GPTModel; src/layer/DecoderLayer.h:38-43;

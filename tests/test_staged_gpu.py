@@ -433,3 +433,36 @@ def test_drop_in_boundary_inside_the_real_reference(built_lib):
         d = (l_ops - ref_logits).abs()
         print(f"[{spec.name}] reference + our ops vs plain reference: mean {float(d.mean()):.3e} max {float(d.max()):.3e}")
         assert float(d.mean()) <= 4e-3 and float(d.max()) <= 8 * ulp
+
+
+# ------------------------------------------------------------------------------------ device sampler (csrc/sampling.cu)
+@pytest.mark.parametrize("V,scale", [(97, 3.0), (5000, 3.0), (151936, 2.0), (32768, 0.05)])
+def test_device_sampler_vs_oracle(built_lib, V, scale):
+    """b200_sample_bf16 against the pinned sampler oracle on bf16 logits (ties included): same drawn index for a set of
+    uniform numbers, except where the oracle's own cdf sits on u·total (or a top-p boundary on top_p) within fp32
+    rounding; and the same call twice gives the same index (integer histogram + fixed-order sums)."""
+    import numpy as np
+    from oracle import sampler_oracle as so
+    from tinygpt_b200 import ops
+    cfgs = [(0.8, 0, 1.0, 0.0), (1.0, 50, 1.0, 0.0), (0.7, 0, 0.9, 0.0), (1.3, 0, 1.0, 0.05), (0.6, 40, 0.95, 0.02),
+            (2.0, 5, 0.5, 0.0), (1.0, 1, 1.0, 0.0), (0.9, 0, 0.0001, 0.0), (1.0, 100000, 0.999, 0.5), (1.0, 7, 0.3, 0.9)]
+    g = torch.Generator().manual_seed(V)
+    logits = (torch.randn(V, generator=g) * scale).to(torch.bfloat16)
+    dev_logits = logits.to(DEV)
+    lf = logits.float().numpy()
+    soft = 0
+    for (T, k, p, mp) in cfgs:
+        want_probs = so.filter_probs(lf, T, k, p, mp)
+        cdf = np.cumsum(want_probs, dtype=np.float32)
+        for u in (0.0003, 0.21, 0.5, 0.77, 0.9996):
+            got = int(ops.sample(dev_logits, T, k, p, mp, u))
+            again = int(ops.sample(dev_logits, T, k, p, mp, u))
+            assert got == again, "device sampler must be deterministic"
+            want = so.draw(want_probs, u)
+            if got != want:
+                soft += 1
+                r = u * float(cdf[-1])
+                near_draw = want_probs[got] > 0 and abs(float(cdf[min(got, want)]) - r) < 2e-5
+                assert near_draw or p < 1.0, (V, (T, k, p, mp), u, got, want)
+    print(f"[sampler V={V}] {soft} of {len(cfgs) * 5} draws differ from the oracle at a rounding boundary")
+    assert soft <= 3

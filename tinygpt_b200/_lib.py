@@ -53,6 +53,8 @@ PROTOTYPES = {
     "b200_embedding_bf16": (I32, [P, P, P, I64, I64, I64, P]),
     "b200_argmax_workspace_bytes": (I64, [I64, I64]),
     "b200_argmax_bf16": (I32, [P, P, I64, I64, P, P]),
+    "b200_sample_workspace_bytes": (I64, []),
+    "b200_sample_bf16": (I32, [P, P, I64, F, I64, F, F, F, P, P]),
     "b200_gemv_fused_bf16": (I32, [P, P, P, I64, I64, I32, P, F, P, P, I32, P]),
     "b200_attn_decode_workspace_bytes": (I64, [I64, I64, I64, I64]),
     "b200_attn_decode_bf16": (I32, [P, P, P, P, F, P, P, I64, P, P, I64, I64, I64, I64, P, P]),
