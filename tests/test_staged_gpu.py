@@ -46,7 +46,7 @@ def _run(spec, prompt, n_new, seed=0):
 @pytest.mark.parametrize("prompt_len", [5, 24], ids=["token-prefill", "gemm-prefill"])
 def test_flagsync_engine_is_bit_identical(built_lib, spec, prompt_len, monkeypatch):
     prompt = torch.randint(0, spec.vocab, (prompt_len,), generator=torch.Generator().manual_seed(1))
-    monkeypatch.delenv("B200_FLAGSYNC", raising=False)
+    monkeypatch.setenv("B200_FLAGSYNC", "0")
     ref = _run(spec, prompt, 24)
     monkeypatch.setenv("B200_FLAGSYNC", "1")
     got = _run(spec, prompt, 24)
@@ -88,7 +88,7 @@ def test_mma_causal_attention_vs_oracle(built_lib, B, S, Hq, Hkv, hd, monkeypatc
     q, k, v = _urand(B, S, Hq, hd, seed=42), _urand(B, S, Hkv, hd, seed=43), _urand(B, S, Hkv, hd, seed=44)
     monkeypatch.setenv("B200_PREFILL_ATTN", "mma")
     got = ops.flash_attention(q.to(DEV), k.to(DEV), v.to(DEV), True).float().cpu()
-    monkeypatch.delenv("B200_PREFILL_ATTN")
+    monkeypatch.setenv("B200_PREFILL_ATTN", "cuda")
     base = ops.flash_attention(q.to(DEV), k.to(DEV), v.to(DEV), True).float().cpu()   # verified CUDA-core kernel
     naive = orc.naive_attention(q, k, v, True)
     err = (got - naive).abs()
@@ -117,7 +117,7 @@ def test_mma_prefill_through_engine(built_lib, spec, S, monkeypatch):
         eng.forward(prompt[:, :cut])
         two = eng.forward(prompt[:, cut:])[0, -1].float().cpu()
         assert float((two - got).abs().max()) <= 2e-2 and float((two - got).abs().mean()) <= 2e-3
-    monkeypatch.delenv("B200_PREFILL_ATTN")
+    monkeypatch.setenv("B200_PREFILL_ATTN", "cuda")
     eng.reset_cache()
     base = eng.forward(prompt)[0, -1].float().cpu()
     base_toks = eng.decode(8).cpu()
@@ -182,7 +182,7 @@ def test_persistent_gemm_vs_oracle_and_v1(built_lib, M, N, K, monkeypatch):
     monkeypatch.setenv("B200_GEMM", "persistent")
     got = ops.gemm(a.to(DEV), w.to(DEV))
     got2 = ops.gemm(a.to(DEV), w.to(DEV))            # TMEM buffers / barriers re-used correctly on a second launch
-    monkeypatch.delenv("B200_GEMM")
+    monkeypatch.setenv("B200_GEMM", "tile")
     base = ops.gemm(a.to(DEV), w.to(DEV))
     assert torch.equal(got, got2)
     if M * N * K <= 2 ** 31:
@@ -244,10 +244,7 @@ def test_l2_prefetch_changes_nothing_but_time(built_lib, flags, monkeypatch):
     runs = []
     for on in (False, True):
         for k, v in flags.items():
-            if on:
-                monkeypatch.setenv(k, v)
-            else:
-                monkeypatch.delenv(k, raising=False)
+            monkeypatch.setenv(k, v if on else "0")
         w = models.synth_weights(spec, seed=0, device=DEV, device_generator=True)
         eng = engine.DecodeEngine(spec, w)
         eng.reset_cache()
@@ -275,9 +272,8 @@ def _tp_fs_worker(rank, world, port, spec_name, shard_attn, q):
         w = models.synth_weights(spec, seed=0)
         prompt = torch.randint(0, spec.vocab, (1, 9), generator=torch.Generator().manual_seed(0)).to(dev)
         out = []
-        for flags in ({}, {"B200_FLAGSYNC": "1", "B200_FLAGSYNC_TP": "1", "B200_L2PF_MB": "8"}):
-            for k in ("B200_FLAGSYNC", "B200_FLAGSYNC_TP", "B200_L2PF_MB"):
-                os.environ.pop(k, None)
+        for flags in ({"B200_FLAGSYNC": "0", "B200_FLAGSYNC_TP": "0", "B200_L2PF_MB": "0"},
+                      {"B200_FLAGSYNC": "1", "B200_FLAGSYNC_TP": "1", "B200_L2PF_MB": "8"}):
             os.environ.update(flags)
             eng = tp.TPDecodeEngine(spec, w, rank, world, dev, shard_attn=shard_attn)
             eng.reset_cache()
@@ -337,7 +333,7 @@ def test_smallk_gemv_is_bit_identical(built_lib, n, k, kind, monkeypatch):
             return ops.gemv_fused(x, w, residual=vec)
         return ops.gemv_fused(x, w, norm_weight=nw, eps=1e-6, silu_mul=True)
 
-    monkeypatch.delenv("B200_GEMV_SMALLK", raising=False)
+    monkeypatch.setenv("B200_GEMV_SMALLK", "0")
     base = run()
     monkeypatch.setenv("B200_GEMV_SMALLK", "1")
     got = run()
@@ -353,10 +349,7 @@ def test_smallk_engine_bit_identical(built_lib, flags, monkeypatch):
         runs = []
         for on in (False, True):
             for k, v in flags.items():
-                if on:
-                    monkeypatch.setenv(k, v)
-                else:
-                    monkeypatch.delenv(k, raising=False)
+                monkeypatch.setenv(k, v if on else "0")
             w = models.synth_weights(spec, seed=0, device=DEV, device_generator=True)
             eng = engine.DecodeEngine(spec, w)
             eng.reset_cache()

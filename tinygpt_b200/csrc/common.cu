@@ -1,6 +1,8 @@
 // common.cu — error state, launch counter, device check and TMA descriptor encoding for the C ABI.
 #include "common.cuh"
 
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -17,6 +19,23 @@ void set_error(const char* fmt, ...) {
 }
 
 const char* last_error() { return t_err; }
+
+bool env_flag(const char* name, bool dflt) {
+  const char* e = std::getenv(name);
+  return (e == nullptr || e[0] == 0) ? dflt : e[0] == '1';
+}
+bool env_choice(const char* name, char yes_initial, bool dflt) {
+  const char* e = std::getenv(name);
+  return (e == nullptr || e[0] == 0) ? dflt : e[0] == yes_initial;
+}
+int env_int(const char* name, int dflt, int lo, int hi) {
+  const char* e = std::getenv(name);
+  if (e == nullptr || e[0] == 0) return dflt;
+  char* end = nullptr;
+  const long v = std::strtol(e, &end, 10);
+  if (end == e) return dflt;
+  return (int)std::max<long>(lo, std::min<long>(hi, v));
+}
 
 // cuTensorMapEncodeTiled is a driver entry point; resolve it through the runtime so the library does not link libcuda
 // (the build machine has no driver).

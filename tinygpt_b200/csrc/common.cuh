@@ -17,6 +17,22 @@ namespace b200 {
 
 // ---------------------------------------------------------------------------------------------------- host errors
 void set_error(const char* fmt, ...);
+
+// ------------------------------------------------------------------------------- opt-in code paths and their defaults
+// Every path that was written without a GPU at hand is chosen by one of these; the environment variable
+// overrides the default BOTH ways ("1"/"0", or the named value), so promoting a path after it has been measured is a
+// one-word change here and the variable then becomes the way to switch it off.
+struct Defaults {
+  static constexpr bool kFlagSync = false;        // B200_FLAGSYNC       completion counters instead of griddepcontrol.wait
+  static constexpr bool kFlagSyncTp = false;      // B200_FLAGSYNC_TP    … also on tensor-parallel engines
+  static constexpr bool kGemvSmallK = false;      // B200_GEMV_SMALLK    register-resident small-k GEMV loop
+  static constexpr int kL2PrefetchMb = 0;         // B200_L2PF_MB        cross-kernel L2 prefetch budget (0 = off)
+  static constexpr bool kPrefillAttnMma = false;  // B200_PREFILL_ATTN   "mma" | "cuda"
+  static constexpr bool kGemmPersistent = false;  // B200_GEMM           "persistent" | "tile"
+};
+bool env_flag(const char* name, bool dflt);                       // unset → dflt; else first character == '1'
+bool env_choice(const char* name, char yes_initial, bool dflt);   // unset → dflt; else first character == yes_initial
+int env_int(const char* name, int dflt, int lo, int hi);          // unset / unparsable → dflt; clamped to [lo, hi]
 extern std::atomic<int64_t> g_launches;
 
 #define B200_CHECK_ARG(cond, ...)     \

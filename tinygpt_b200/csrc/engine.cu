@@ -417,12 +417,11 @@ static int engine_build(const b200_model_desc* desc, const b200_weight_table* w,
   e->use_graph = !(env && env[0] == '1');
   env = std::getenv("B200_NO_PDL");
   e->use_pdl = !(env && env[0] == '1');
-  env = std::getenv("B200_FLAGSYNC");
-  // tensor-parallel engines take it only when asked twice (B200_FLAGSYNC=1 B200_FLAGSYNC_TP=1): validate on one GPU first
-  const char* env_tp = std::getenv("B200_FLAGSYNC_TP");
-  e->use_flagsync = (env && env[0] == '1') && e->use_pdl && (world == 1 || (env_tp && env_tp[0] == '1'));
-  env = std::getenv("B200_L2PF_MB");
-  if (env) e->l2pf_bytes = (int64_t)std::max(0, std::min(64, std::atoi(env))) << 20;
+  // tensor-parallel engines take flag-sync only when asked twice (B200_FLAGSYNC=1 B200_FLAGSYNC_TP=1): validate on one
+  // GPU first
+  e->use_flagsync = env_flag("B200_FLAGSYNC", Defaults::kFlagSync) && e->use_pdl &&
+                    (world == 1 || env_flag("B200_FLAGSYNC_TP", Defaults::kFlagSyncTp));
+  e->l2pf_bytes = (int64_t)env_int("B200_L2PF_MB", Defaults::kL2PrefetchMb, 0, 64) << 20;
   env = std::getenv("B200_NO_PREFILL_GEMM");
   e->use_prefill_gemm = !(env && env[0] == '1');
   e->final_norm_w = w->final_norm;

@@ -400,8 +400,7 @@ int launch_gemm_bf16(void* C, const void* A, const void* B, int64_t M, int64_t N
   }
   CUtensorMap ta, tb;
   int rc;
-  const char* mode = std::getenv("B200_GEMM");
-  if (mode != nullptr && mode[0] == 'p') {  // "persistent": opt-in, see gemm_tcgen05_persistent_kernel
+  if (env_choice("B200_GEMM", 'p', Defaults::kGemmPersistent)) {  // "persistent" | "tile", see the persistent kernel
     static std::once_flag p_once;
     static cudaError_t p_err = cudaSuccess;
     static int sms = 0;

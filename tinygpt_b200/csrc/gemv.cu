@@ -675,8 +675,7 @@ int gemv_make_plan(GemvPlan* plan, const void* W, int64_t rows_total, int64_t n,
   plan->p.stages = stages;
   plan->p.tp_world = 1;
   // opt-in register-resident small-k consumer loop (see gemv_stream_kernel SMALLK)
-  const char* sk = std::getenv("B200_GEMV_SMALLK");
-  plan->smallk = sk != nullptr && sk[0] == '1' && sh.rpw == 1 && sh.k_pad <= 1024 && ctas_per_sm == 1 &&
+  plan->smallk = env_flag("B200_GEMV_SMALLK", Defaults::kGemvSmallK) && sh.rpw == 1 && sh.k_pad <= 1024 && ctas_per_sm == 1 &&
                  (sh.rbs + g - 1) / g <= kSmallkMaxRb && pick_smallk(nseg, pro, epi, false) != nullptr;
   B200_CHECK_ARG(pick(sh.rpw, nseg, pro, epi) != nullptr, "gemv: no kernel for nseg=%d pro=%d epi=%d", nseg, pro, epi);
   B200_CHECK_ARG(plan->smem <= kGemvMaxSmem + 4096, "gemv: k=%lld needs %d bytes of shared memory", (long long)k,

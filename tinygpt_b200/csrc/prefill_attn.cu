@@ -275,8 +275,7 @@ int launch_pf(const PrefillAttnParams& p, int B, cudaStream_t st) {
 }  // namespace
 
 bool prefill_attn_mma_enabled() {  // read per call (a getenv per prefill launch is noise; tests toggle it in-process)
-  const char* e = std::getenv("B200_PREFILL_ATTN");
-  return e != nullptr && e[0] == 'm';  // "mma"
+  return env_choice("B200_PREFILL_ATTN", 'm', Defaults::kPrefillAttnMma);  // "mma" | "cuda"
 }
 
 // Engine prefill: q inside the merged qkv rows [S, qdim + 2 kvdim], K/V in the in-place cache [max_ctx, Hkv, hd].

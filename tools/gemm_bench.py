@@ -25,10 +25,7 @@ for M in (512, 2048):
         ws = [(torch.randn(N, K, device="cuda") * 0.02).to(torch.bfloat16) for _ in range(8)]  # 8 × ≥ 8 MB ≫ reuse in L2
         row = [f"M={M:5d} {name:8s} N={N:6d} K={K:5d}"]
         for mode in ("tile", "persistent"):
-            if mode == "persistent":
-                os.environ["B200_GEMM"] = "persistent"
-            else:
-                os.environ.pop("B200_GEMM", None)
+            os.environ["B200_GEMM"] = mode
             for w in ws[:3]:
                 ops.gemm(a, w)
             torch.cuda.synchronize()
