@@ -396,10 +396,10 @@ def run_ours(args):
                        "; hidden-vector reductions fused into the GEMV kernels over NVLink peer memory"
                        if tp_mode else f"{world} independent replicas (one sequence per GPU, no collective)"),
                    "l2": "weights 0.99 GB > 126 MB L2: re-streamed from HBM every token, no explicit flush",
-                   "kernel_sync": ("per-op completion counters (B200_FLAGSYNC=1)"
-                                   if os.environ.get("B200_FLAGSYNC") == "1" and world == 1 else
+                   "kernel_sync": ("per-op completion counters (flag-sync)" if eng.options["flag_sync"] else
                                    "programmatic dependent launch (griddepcontrol.wait)"),
-                   "l2_prefetch_mb": int(os.environ.get("B200_L2PF_MB", "0") or 0)},
+                   "l2_prefetch_mb": eng.options["l2_prefetch_mb"],
+                   "gemv_smallk": os.environ.get("B200_GEMV_SMALLK", "default")},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src,
                      "kernel": f"whole decode token ({eng.launches_per_token} launches, PDL-chained; "

@@ -250,6 +250,9 @@ int64_t b200_engine_debug_trace(b200_engine* eng, uint64_t* out_host, int64_t ma
 /* Host-side mirrors (no device access): tokens consumed so far, and kernels per decoded token. */
 int64_t b200_engine_position(const b200_engine* eng);
 int64_t b200_engine_launches_per_token(const b200_engine* eng);
+/* Which code paths this engine was built with (environment / defaults at create time): bit 0 CUDA graph, bit 1
+ * programmatic dependent launch, bit 2 flag synchronisation, bit 3 batched GEMM prefill, bits 8-15 L2 prefetch MB. */
+int64_t b200_engine_options(const b200_engine* eng);
 /* Algorithmic HBM bytes one decode step reads on THIS rank at context length ctx (weights once + KV + logits). */
 int64_t b200_engine_bytes_per_token(const b200_engine* eng, int64_t ctx);
 

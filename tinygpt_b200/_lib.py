@@ -70,6 +70,7 @@ PROTOTYPES = {
     "b200_engine_generated": (I64, [P]),
     "b200_engine_set_mailbox": (I32, [P, P, I64, P]),
     "b200_engine_launches_per_token": (I64, [P]),
+    "b200_engine_options": (I64, [P]),
     "b200_engine_bytes_per_token": (I64, [P, I64]),
     "b200_tp_window_bytes": (I64, [C.POINTER(ModelDesc)]),
     "b200_tp_window_create": (I32, [I64, C.POINTER(P), C.c_char_p]),

@@ -878,6 +878,11 @@ int64_t b200_engine_debug_trace(b200_engine* e, uint64_t* out_host, int64_t max_
   return n;
 }
 int64_t b200_engine_launches_per_token(const b200_engine* e) { return e ? e->launches_per_token : -1; }
+int64_t b200_engine_options(const b200_engine* e) {
+  if (!e) return -1;
+  return (e->use_graph ? 1 : 0) | (e->use_pdl ? 2 : 0) | (e->use_flagsync ? 4 : 0) | (e->use_prefill_gemm ? 8 : 0) |
+         ((e->l2pf_bytes >> 20) << 8);
+}
 
 int64_t b200_engine_bytes_per_token(const b200_engine* e, int64_t ctx) {
   if (!e) return -1;

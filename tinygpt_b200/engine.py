@@ -96,6 +96,13 @@ class DecodeEngine:
     def launches_per_token(self) -> int:
         return int(lib().b200_engine_launches_per_token(self._h))
 
+    @property
+    def options(self) -> dict:
+        """Code paths this engine was built with (b200_engine_options)."""
+        o = int(lib().b200_engine_options(self._h))
+        return {"cuda_graph": bool(o & 1), "pdl": bool(o & 2), "flag_sync": bool(o & 4), "gemm_prefill": bool(o & 8),
+                "l2_prefetch_mb": (o >> 8) & 0xFF}
+
     def bytes_per_token(self, ctx: int) -> int:
         return int(lib().b200_engine_bytes_per_token(self._h, ctx))
 
