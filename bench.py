@@ -395,7 +395,8 @@ def run_ours(args):
                        ("sharded" if eng.shard_attn else "replicated (head counts do not divide)") +
                        "; hidden-vector reductions fused into the GEMV kernels over NVLink peer memory"
                        if tp_mode else f"{world} independent replicas (one sequence per GPU, no collective)"),
-                   "l2": "weights 0.99 GB > 126 MB L2: re-streamed from HBM every token, no explicit flush",
+                   "l2": f"weights {eng.bytes_per_token(0) / 1e9:.2f} GB per GPU > 126 MB L2: re-streamed from HBM "
+                         "every token, no explicit flush",
                    "kernel_sync": ("per-op completion counters (flag-sync)" if eng.options["flag_sync"] else
                                    "programmatic dependent launch (griddepcontrol.wait)"),
                    "l2_prefetch_mb": eng.options["l2_prefetch_mb"],
