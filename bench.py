@@ -395,8 +395,10 @@ def run_ours(args):
                        ("sharded" if eng.shard_attn else "replicated (head counts do not divide)") +
                        "; hidden-vector reductions fused into the GEMV kernels over NVLink peer memory"
                        if tp_mode else f"{world} independent replicas (one sequence per GPU, no collective)"),
-                   "l2": f"weights {eng.bytes_per_token(0) / 1e9:.2f} GB per GPU > 126 MB L2: re-streamed from HBM "
-                         "every token, no explicit flush",
+                   "l2": (f"weights {eng.bytes_per_token(0) / 1e9:.2f} GB per GPU > 126 MB L2: re-streamed from HBM "
+                          "every token, no explicit flush") if eng.bytes_per_token(0) > 126e6 else
+                         (f"weights {eng.bytes_per_token(0) / 1e6:.0f} MB per GPU fit in the 126 MB L2 and are NOT "
+                          "flushed between tokens: the HBM roofline does not bound this configuration"),
                    "kernel_sync": ("per-op completion counters (flag-sync)" if eng.options["flag_sync"] else
                                    "programmatic dependent launch (griddepcontrol.wait)"),
                    "l2_prefetch_mb": eng.options["l2_prefetch_mb"],
