@@ -29,8 +29,9 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden; these are its only exports */
 #endif
 
-/* 2: + b200_engine_set_mailbox, b200_engine_generated (additive; version-1 callers keep working) */
-#define B200_ABI_VERSION 2
+/* 2: + b200_engine_set_mailbox, b200_engine_generated;  3: + b200_sample_bf16, b200_sample_workspace_bytes,
+ * b200_engine_set_sampler, b200_engine_options.  All additive: callers of an older version keep working. */
+#define B200_ABI_VERSION 3
 
 typedef enum b200_status {
   B200_OK = 0,
@@ -239,6 +240,12 @@ int b200_engine_last_token(b200_engine* eng, int64_t* token_out, void* stream);
  * cudaHostRegister; with unified addressing the host pointer itself), zero-initialised, alive until the mailbox is
  * cleared with ring = NULL or the engine destroyed.  Re-captures the per-token graphs; single-GPU engines only. */
 int b200_engine_set_mailbox(b200_engine* eng, uint64_t* ring_host_mapped, int64_t capacity, void* stream);
+/* SamplerConfig of the generate loop [ref: src/engine/Sampler.h:13-22, Sampler.cpp:14-21]: with any knob set
+ * (temperature > 0, top_k > 0, top_p < 1, min_p > 0) the engine picks every token with the device sampler
+ * (b200_sample_bf16's kernels, uniform number = Philox4x32-10(seed, tokens generated so far)); all knobs off = greedy
+ * argmax again.  Re-captures the per-token graph; single-GPU engines only.  Staged. */
+int b200_engine_set_sampler(b200_engine* eng, float temperature, int64_t top_k, float top_p, float min_p, uint64_t seed,
+                            void* stream);
 /* Host-side mirror: how many tokens this engine has generated (= n of the most recently enqueued token). */
 int64_t b200_engine_generated(const b200_engine* eng);
 

@@ -139,3 +139,19 @@ def test_argument_checks():
         eng.generate_async([], 3)
     with pytest.raises(B200Error):
         eng.generate_async([1], 0)
+
+
+def test_philox_known_answers():
+    """DecodeEngine.philox_uniform mirrors sampling.cu's Philox4x32-10; the round function is checked against the
+    Random123 known-answer vectors (counter, key all zero / all ones → first output word)."""
+    M = 0xFFFFFFFF
+    assert engine.DecodeEngine.philox_uniform(0, 0) == ((0x6627E8D5 >> 8) + 0.5) / 16777216.0
+    # all-ones counter needs c2 = c3 = M, which the engine never uses: check the round function directly
+    c, k = [M, M, M, M], [M, M]
+    for _ in range(10):
+        p0, p1 = 0xD2511F53 * c[0], 0xCD9E8D57 * c[2]
+        c = [((p1 >> 32) ^ c[1] ^ k[0]) & M, p1 & M, ((p0 >> 32) ^ c[3] ^ k[1]) & M, p0 & M]
+        k = [(k[0] + 0x9E3779B9) & M, (k[1] + 0xBB67AE85) & M]
+    assert c == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    us = [engine.DecodeEngine.philox_uniform(7, n) for n in range(2000)]
+    assert all(0.0 < u < 1.0 for u in us) and 0.45 < sum(us) / len(us) < 0.55 and len(set(us)) > 1990

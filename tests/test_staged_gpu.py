@@ -459,3 +459,41 @@ def test_device_sampler_vs_oracle(built_lib, V, scale):
                 assert near_draw or p < 1.0, (V, (T, k, p, mp), u, got, want)
     print(f"[sampler V={V}] {soft} of {len(cfgs) * 5} draws differ from the oracle at a rounding boundary")
     assert soft <= 3
+
+
+def test_engine_sampler_replays_on_the_host(built_lib):
+    """b200_engine_set_sampler: every token the engine draws equals the oracle's draw from the SAME logits with the SAME
+    uniform number (Philox(seed, tokens generated so far), mirrored on the host), up to a rounding boundary; switching
+    the sampler off restores greedy decoding; sampled tokens also arrive through the mailbox."""
+    import numpy as np
+    from oracle import sampler_oracle as so
+    from tinygpt_b200._lib import lib
+    spec = models.TINY_QWEN2.with_ctx(128)
+    w = {k: v.to(DEV) for k, v in models.synth_weights(spec, seed=3, std=0.05).items()}
+    eng = engine.DecodeEngine(spec, w)
+    prompt = torch.randint(0, spec.vocab, (1, 9), generator=torch.Generator().manual_seed(1)).to(DEV)
+    greedy = eng.generate_sync(prompt.view(-1).tolist(), 12).tolist()
+    cfg = dict(temperature=0.9, top_k=40, top_p=0.95, min_p=0.01)
+    eng.set_sampler(seed=1234, **cfg)
+    eng.reset_cache()
+    ids, soft = prompt, 0
+    for step in range(16):
+        n = int(lib().b200_engine_generated(eng._h))
+        logits = eng.forward(ids)[0, -1].float().cpu().numpy()
+        tok = torch.empty(1, dtype=torch.int64, device=DEV)
+        lib().b200_engine_last_token(eng._h, tok.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        got = int(tok.item())
+        u = engine.DecodeEngine.philox_uniform(1234, n)
+        want = so.sample(logits, cfg["temperature"], cfg["top_k"], cfg["top_p"], cfg["min_p"], u)
+        if got != want:
+            soft += 1
+            probs = so.filter_probs(logits, cfg["temperature"], cfg["top_k"], cfg["top_p"], cfg["min_p"])
+            cdf = np.cumsum(probs, dtype=np.float32)
+            assert abs(float(cdf[min(got, want)]) - u * float(cdf[-1])) < 2e-5 or probs[got] > 0, (step, got, want, u)
+        ids = tok.view(1, 1)
+    assert soft <= 1
+    out, reason = eng.generate_async(prompt.view(-1).tolist(), 10, lookahead=2)     # sampled tokens through the mailbox
+    assert len(out) == 10 and all(0 <= t < spec.vocab for t in out)
+    eng.set_sampler()                                                                 # all knobs off → greedy again
+    assert eng.generate_sync(prompt.view(-1).tolist(), 12).tolist() == greedy
+    eng.close()

@@ -69,6 +69,7 @@ PROTOTYPES = {
     "b200_engine_position": (I64, [P]),
     "b200_engine_generated": (I64, [P]),
     "b200_engine_set_mailbox": (I32, [P, P, I64, P]),
+    "b200_engine_set_sampler": (I32, [P, F, I64, F, F, C.c_uint64, P]),
     "b200_engine_launches_per_token": (I64, [P]),
     "b200_engine_options": (I64, [P]),
     "b200_engine_bytes_per_token": (I64, [P, I64]),

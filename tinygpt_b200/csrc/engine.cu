@@ -74,6 +74,13 @@ struct b200_engine {
   bool use_pdl = true;
   // opt-in (B200_FLAGSYNC=1, single GPU): kernels of a token wait on per-op completion counters instead of
   // griddepcontrol.wait (common.cuh FlagSync).  One 128-byte line per op; fs_epoch counts completed tokens.
+  // sampler (b200_engine_set_sampler): when active the last kernels of a head token are the device sampler instead of
+  // the argmax; u = Philox(seed, tokens generated so far)
+  bool sampler_on = false;
+  float s_temperature = 0.f, s_top_p = 1.f, s_min_p = 0.f;
+  int64_t s_top_k = 0;
+  unsigned long long s_seed = 0;
+  void* sample_ws = nullptr;
   // async token pipeline (b200_engine_set_mailbox): ring in pinned host memory the argmax kernel posts tokens into
   unsigned long long* mailbox = nullptr;
   unsigned long long mailbox_cap = 1;
@@ -275,7 +282,13 @@ static int engine_launch_token(b200_engine* e, cudaStream_t st, bool with_head) 
       pub.epoch_inc = fs ? e->fs_epoch : nullptr;  // full dependency on the lm_head: every CTA of the token is done
       pub.mailbox = e->mailbox;
       pub.mailbox_cap = e->mailbox_cap;
-      if ((rc = launch_argmax(amax, e->logits, 1, e->V_l, e->argmax_ws, st, false, &pub)) != B200_OK) return rc;
+      if (e->sampler_on) {
+        if ((rc = launch_sample(nullptr, e->logits, e->V_l, e->s_temperature, e->s_top_k, e->s_top_p, e->s_min_p, 0.f,
+                                e->sample_ws, st, &pub, e->s_seed, true)) != B200_OK)
+          return rc;
+      } else if ((rc = launch_argmax(amax, e->logits, 1, e->V_l, e->argmax_ws, st, false, &pub)) != B200_OK) {
+        return rc;
+      }
     } else {
       pub.tp_world = e->tp_world;
       pub.tp_index_offset = (int64_t)e->tp_rank * e->V_l;
@@ -466,6 +479,7 @@ static int engine_build(const b200_model_desc* desc, const b200_weight_table* w,
   const size_t o_epoch = take(16);
   const size_t o_fsctr = take((size_t)(5 * d.layers + 3) * 128);
   const size_t o_fsepoch = take(16);
+  const size_t o_sample = take((size_t)sample_workspace_bytes());
   e->arena_bytes = off;
   B200_CUDA(cudaMalloc((void**)&e->arena, e->arena_bytes));
   // zero only the small control region + activations (the KV cache is always written before it is read)
@@ -488,6 +502,7 @@ static int engine_build(const b200_model_desc* desc, const b200_weight_table* w,
   e->gen_count = (unsigned long long*)(e->arena + o_cnt);
   e->fs_ctr = (unsigned long long*)(e->arena + o_fsctr);
   e->fs_epoch = (unsigned long long*)(e->arena + o_fsepoch);
+  e->sample_ws = (void*)(e->arena + o_sample);
 
   // ---- shared-memory budgets.  PDL keeps two consecutive kernels resident on an SM, and a kernel's TMA ring is
   // filled while its predecessors still run; the deeper the ring, the more of a layer's weights are already on chip
@@ -710,6 +725,9 @@ static int engine_prefill(b200_engine* e, const int64_t* ids, int64_t S, cudaStr
   pub.gen_cap = e->gen_cap;
   pub.mailbox = e->mailbox;
   pub.mailbox_cap = e->mailbox_cap;
+  if (e->sampler_on)
+    return launch_sample(nullptr, e->logits, e->V_l, e->s_temperature, e->s_top_k, e->s_top_p, e->s_min_p, 0.f,
+                         e->sample_ws, st, &pub, e->s_seed, true);
   return launch_argmax(amax, e->logits, 1, e->V_l, e->argmax_ws, st, false, &pub);
 }
 
@@ -837,6 +855,35 @@ int b200_engine_last_token(b200_engine* e, int64_t* token_out, void* stream) {
 
 int64_t b200_engine_position(const b200_engine* e) { return e ? e->h_pos : -1; }
 int64_t b200_engine_generated(const b200_engine* e) { return e ? e->h_gen : -1; }
+
+int b200_engine_set_sampler(b200_engine* e, float temperature, int64_t top_k, float top_p, float min_p, uint64_t seed,
+                            void* stream) {
+  using namespace b200;
+  B200_CHECK_ARG(e, "engine_set_sampler: null engine");
+  B200_CHECK_ARG(temperature >= 0.f && top_p >= 0.f && min_p >= 0.f && min_p <= 1.f && top_k >= 0,
+                 "engine_set_sampler: parameter out of range");
+  if (e->tp_world > 1) {
+    set_error("engine_set_sampler: tensor-parallel engines pick the token from vocabulary shards; sampler not built");
+    return B200_ERR_UNSUPPORTED;
+  }
+  // Sampler::Sampler (src/engine/Sampler.cpp:14-21): sampling is on as soon as any of the four knobs is set
+  const bool on = temperature > 0.f || top_k > 0 || top_p < 1.f || min_p > 0.f;
+  B200_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  e->sampler_on = on;
+  e->s_temperature = temperature;
+  e->s_top_k = top_k;
+  e->s_top_p = top_p;
+  e->s_min_p = min_p;
+  e->s_seed = seed;
+  if (e->use_graph) {
+    cudaGraphExec_t fresh = nullptr;
+    int rc = engine_capture(e, true, &fresh);
+    if (rc != B200_OK) return rc;
+    if (e->g_step) cudaGraphExecDestroy(e->g_step);
+    e->g_step = fresh;
+  }
+  return B200_OK;
+}
 
 int b200_engine_set_mailbox(b200_engine* e, uint64_t* ring, int64_t capacity, void* stream) {
   using namespace b200;

@@ -35,6 +35,12 @@ struct ArgmaxPublish {
 int launch_argmax(int64_t* idx, const void* logits, int64_t rows, int64_t V, void* workspace, cudaStream_t st,
                   bool pdl, const ArgmaxPublish* pub);
 
+// ---- device sampler (sampling.cu): temperature / top-k / top-p / min-p + inverse-CDF draw without sorting
+int64_t sample_workspace_bytes();
+int launch_sample(int64_t* token_out, const void* logits, int64_t V, float temperature, int64_t top_k, float top_p,
+                  float min_p, float u, void* workspace, cudaStream_t st, const ArgmaxPublish* pub,
+                  unsigned long long rng_seed, bool device_rng);
+
 // ---- tcgen05 prefill GEMM (gemm.cu)
 int launch_gemm_bf16(void* C, const void* A, const void* B, int64_t M, int64_t N, int64_t K, cudaStream_t st);
 

@@ -196,11 +196,34 @@ __global__ void __launch_bounds__(kPlanThreads) sample_plan_kernel(const unsigne
 // One CTA over the vocabulary in index order.  Pass 0: total probability.  Pass 1: first index whose inclusive cdf
 // reaches r = u · total.  Thread t owns kDrawItems consecutive entries of each chunk, chunks are visited in order and a
 // running carry (cdf so far, partial-bin entries seen so far) crosses chunks, so the cdf is the index-order cdf.
+// Philox4x32-10 (Salmon et al., SC'11) written out here so that the host can reproduce the engine's uniform numbers:
+// counter = {n lo, n hi, 0, 0} with n = tokens generated so far, key = seed; u = (x0 >> 8 + 0.5) · 2^-24 ∈ (0, 1).
+__device__ __forceinline__ float philox_uniform(unsigned long long seed, unsigned long long n) {
+  unsigned int c0 = (unsigned int)n, c1 = (unsigned int)(n >> 32), c2 = 0u, c3 = 0u;
+  unsigned int k0 = (unsigned int)seed, k1 = (unsigned int)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned int hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const unsigned int hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const unsigned int n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0;
+    c1 = lo1;
+    c2 = n2;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return ((float)(c0 >> 8) + 0.5f) * (1.0f / 16777216.0f);
+}
+
+// `pub` (engine only): publish the drawn token like the engine's argmax does (next step's input, on-device log, position,
+// token mailbox); `rng_seed_valid`: draw u on the device from Philox(seed, tokens generated so far) instead of `u`.
 __global__ void __launch_bounds__(kDrawThreads) sample_draw_kernel(const __nv_bfloat16* __restrict__ logits, int64_t V,
                                                                    float temperature, float u,
                                                                    const int* __restrict__ kept,
                                                                    const SamplePlan* __restrict__ plan,
-                                                                   int64_t* __restrict__ out) {
+                                                                   int64_t* __restrict__ out, const ArgmaxPublish pub,
+                                                                   unsigned long long rng_seed, int rng_seed_valid) {
   using ScanD = cub::BlockScan<double, kDrawThreads>;
   using ScanI = cub::BlockScan<int, kDrawThreads>;
   __shared__ union {
@@ -219,6 +242,7 @@ __global__ void __launch_bounds__(kDrawThreads) sample_draw_kernel(const __nv_bf
   const int t = threadIdx.x;
   constexpr int kChunk = kDrawThreads * kDrawItems;
   double total = 0.0;
+  if (rng_seed_valid) u = philox_uniform(rng_seed, *pub.gen_count);
 
   for (int pass = 0; pass < 2; ++pass) {
     if (t == 0) {
@@ -291,7 +315,20 @@ __global__ void __launch_bounds__(kDrawThreads) sample_draw_kernel(const __nv_bf
   if (t == 0) {
     long long pick = s_pick;
     if (!(total > 0.0) || pick < 0) pick = (total > 0.0) ? (long long)(V - 1) : 0;   // the reference returns 0 when total ≤ 0
-    out[0] = pick;
+    if (out != nullptr) out[0] = pick;
+    if (pub.cur_tok != nullptr) {   // same publication as argmax_kernel (ops.cu)
+      *pub.cur_tok = pick;
+      if (pub.pos != nullptr) *pub.pos += 1;
+      if (pub.epoch_inc != nullptr) *pub.epoch_inc += 1ull;
+      const unsigned long long c = *pub.gen_count;
+      pub.gen_log[c % (unsigned long long)pub.gen_cap] = pick;
+      *pub.gen_count = c + 1;
+      if (pub.mailbox != nullptr) {
+        const unsigned long long word = (((c + 1ull) & 0xffffffffull) << 32) | (unsigned long long)(unsigned int)pick;
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(pub.mailbox + (c % pub.mailbox_cap)), "l"(word)
+                     : "memory");
+      }
+    }
   }
 }
 
@@ -300,8 +337,10 @@ __global__ void __launch_bounds__(kDrawThreads) sample_draw_kernel(const __nv_bf
 int64_t sample_workspace_bytes() { return (int64_t)kBins * 4 /*hist*/ + (int64_t)kBins * 4 /*kept*/ + 256 /*plan*/; }
 
 int launch_sample(int64_t* token_out, const void* logits, int64_t V, float temperature, int64_t top_k, float top_p,
-                  float min_p, float u, void* workspace, cudaStream_t st) {
-  B200_CHECK_ARG(token_out && logits && workspace && V > 0 && V < (1ll << 31), "sample: bad arguments");
+                  float min_p, float u, void* workspace, cudaStream_t st, const ArgmaxPublish* pub,
+                  unsigned long long rng_seed, bool device_rng) {
+  B200_CHECK_ARG((token_out || pub) && logits && workspace && V > 0 && V < (1ll << 31), "sample: bad arguments");
+  B200_CHECK_ARG(!device_rng || (pub && pub->gen_count), "sample: the device RNG counts the engine's generated tokens");
   B200_CHECK_ARG(temperature >= 0.f && top_p >= 0.f && min_p >= 0.f && min_p <= 1.f && u >= 0.f && u <= 1.f,
                  "sample: temperature/top_p/min_p/u out of range");
   B200_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "sample: workspace must be 256-byte aligned");
@@ -313,7 +352,8 @@ int launch_sample(int64_t* token_out, const void* logits, int64_t V, float tempe
   g_launches.fetch_add(3);
   sample_hist_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)logits, V, hist);
   sample_plan_kernel<<<1, kPlanThreads, 0, st>>>(hist, V, temperature, top_k, top_p, min_p, kept, plan);
-  sample_draw_kernel<<<1, kDrawThreads, 0, st>>>((const __nv_bfloat16*)logits, V, temperature, u, kept, plan, token_out);
+  sample_draw_kernel<<<1, kDrawThreads, 0, st>>>((const __nv_bfloat16*)logits, V, temperature, u, kept, plan, token_out,
+                                                 pub ? *pub : ArgmaxPublish{}, rng_seed, device_rng ? 1 : 0);
   B200_CUDA(cudaGetLastError());
   return B200_OK;
 }
@@ -328,7 +368,8 @@ int b200_sample_bf16(int64_t* token_out, const void* logits, int64_t V, float te
                      float min_p, float u, void* workspace, void* stream) {
   int rc = b200_device_check();
   if (rc != B200_OK) return rc;
-  return b200::launch_sample(token_out, logits, V, temperature, top_k, top_p, min_p, u, workspace, (cudaStream_t)stream);
+  return b200::launch_sample(token_out, logits, V, temperature, top_k, top_p, min_p, u, workspace, (cudaStream_t)stream,
+                             nullptr, 0ull, false);
 }
 
 }  // extern "C"

@@ -168,6 +168,27 @@ class DecodeEngine:
         torch.cuda.current_stream(self.device).synchronize()
         return pinned_out[:max_new_tokens].clone()
 
+    # ------------------------------------------------------------------------------------------------ sampler
+    def set_sampler(self, temperature: float = 0.0, top_k: int = 0, top_p: float = 1.0, min_p: float = 0.0,
+                    seed: int = 0) -> None:
+        """SamplerConfig of the reference's generate loop (src/engine/Sampler.h:13-22).  Any knob set ⇒ every token is
+        drawn by the device sampler with u = philox_uniform(seed, tokens generated so far); all off ⇒ greedy."""
+        check(lib().b200_engine_set_sampler(self._h, float(temperature), int(top_k), float(top_p), float(min_p),
+                                            int(seed) & 0xFFFFFFFFFFFFFFFF, self._stream()), "b200_engine_set_sampler")
+
+    @staticmethod
+    def philox_uniform(seed: int, n: int) -> float:
+        """The uniform number the engine's sampler uses for its n-th generated token (n counts from 0): Philox4x32-10,
+        counter {n lo, n hi, 0, 0}, key = seed; u = ((x0 >> 8) + 0.5)·2^-24.  Host mirror of sampling.cu."""
+        M = 0xFFFFFFFF
+        c = [n & M, (n >> 32) & M, 0, 0]
+        k = [seed & M, (seed >> 32) & M]
+        for _ in range(10):
+            p0, p1 = 0xD2511F53 * c[0], 0xCD9E8D57 * c[2]
+            c = [((p1 >> 32) ^ c[1] ^ k[0]) & M, p1 & M, ((p0 >> 32) ^ c[3] ^ k[1]) & M, p0 & M]
+            k = [(k[0] + 0x9E3779B9) & M, (k[1] + 0xBB67AE85) & M]
+        return ((c[0] >> 8) + 0.5) / 16777216.0
+
     # ----------------------------------------------------------------------------------------- generateAsync
     def set_mailbox(self, capacity: int = 64) -> torch.Tensor:
         """Attach a token mailbox: a zeroed ring of `capacity` 8-byte words in pinned host memory that the argmax kernel

@@ -18,7 +18,7 @@ echo "== staged tests"
 # one process per group: a trap (sticky CUDA error) in one staged path must not mask the others
 : > "$OUT/staged_tests.log"
 for grp in flagsync_engine flagsync_full mma_causal mma_prefill persistent_gemm prefill_chunk generate_async loader_cuda \
-           l2_prefetch smallk_gemv smallk_engine tp2_flagsync reference_cuda drop_in_boundary device_sampler; do
+           l2_prefetch smallk_gemv smallk_engine tp2_flagsync reference_cuda drop_in_boundary device_sampler engine_sampler; do
   echo "---- $grp" >> "$OUT/staged_tests.log"
   B200_STAGED=1 timeout 600 python -m pytest tests/test_staged_gpu.py -m gpu -q -rA -s -k "$grp" >> "$OUT/staged_tests.log" 2>&1
   echo "$grp: $(grep -E '^[0-9]+ (passed|failed)|passed|failed|error' "$OUT/staged_tests.log" | tail -n 1)"
