@@ -136,3 +136,180 @@ def test_key_transform_is_order_preserving_and_invertible():
     idx = np.argsort(keys[ok].astype(np.int64), kind="stable")
     sv = vals[ok][idx]
     assert (np.diff(sv) >= 0).all()      # −0.0 sorts just below +0.0, both compare equal as floats
+
+
+# --------------------------------------------------------------------------------- thread-level emulation of sampling.cu
+PLAN_THREADS, BINS_PER_THREAD = 512, 128
+DRAW_THREADS, DRAW_ITEMS = 512, 8
+
+
+def emulate_plan_kernel(hist, V, temperature, top_k, top_p, min_p):
+    """sample_plan_kernel statement by statement: thread t owns bins hi − j (hi = 65535 − 128 t, j = 0…127) and walks
+    them downwards; block scans / reductions are exclusive prefix sums / sums over the per-thread values in thread
+    order (what cub::BlockScan / BlockReduce deliver)."""
+    hist = hist.astype(np.int64)
+    T = PLAN_THREADS
+    hi = [65535 - t * BINS_PER_THREAD for t in range(T)]
+    kept = np.zeros(65536, dtype=np.int64)
+
+    def sv(key):
+        v = key_value(np.array([key], dtype=np.uint16))[0]
+        return F32(v / F32(temperature)) if temperature > 0 else F32(v)
+
+    my_max = [-1] * T
+    for t in range(T):
+        for j in range(BINS_PER_THREAD):
+            if hist[hi[t] - j] != 0:
+                my_max[t] = hi[t] - j
+                break
+    kmax = max(my_max)
+    vmax = sv(kmax)
+
+    def e_of(key):
+        with np.errstate(all="ignore"):
+            return F32(np.exp(F32(sv(key) - vmax)))
+
+    use_k = 0 < top_k < V
+    mine = [int(sum(hist[hi[t] - j] for j in range(BINS_PER_THREAD))) for t in range(T)]
+    before = np.concatenate([[0], np.cumsum(mine)[:-1]])
+    for t in range(T):
+        b = int(before[t])
+        for j in range(BINS_PER_THREAD):
+            c = int(hist[hi[t] - j])
+            k = c
+            if use_k:
+                k = min(max(top_k - b, 0), c)
+            kept[hi[t] - j] = k
+            b += c
+
+    def block_z():
+        tot = 0.0
+        for t in range(T):
+            m = 0.0
+            for j in range(BINS_PER_THREAD):
+                k = int(kept[hi[t] - j])
+                if k:
+                    m += k * float(e_of(hi[t] - j))
+            tot += m
+        return tot
+
+    if top_p < 1.0:
+        zf = F32(block_z())
+        mass = []
+        for t in range(T):
+            m = 0.0
+            for j in range(BINS_PER_THREAD):
+                k = int(kept[hi[t] - j])
+                if k:
+                    m += k * float(F32(e_of(hi[t] - j) / zf))
+            mass.append(m)
+        before = np.concatenate([[0.0], np.cumsum(mass)[:-1]])
+        for t in range(T):
+            b = float(before[t])
+            for j in range(BINS_PER_THREAD):
+                key = hi[t] - j
+                k = int(kept[key])
+                if k == 0:
+                    continue
+                p = F32(e_of(key) / zf)
+                m = int(np.floor((float(F32(top_p)) - b) / float(p) + 1e-9))
+                m = min(max(m, 0), k)
+                if key == kmax and m < 1:
+                    m = 1
+                kept[key] = m
+                b += k * float(p)
+    if min_p > 0:
+        zf = F32(block_z())
+        thr = F32(F32(e_of(kmax) / zf) * F32(min_p))
+        for key in np.nonzero(kept)[0]:
+            if F32(e_of(int(key)) / zf) < thr:
+                kept[key] = 0
+    z = block_z()
+    partial = [(int(k), int(kept[k])) for k in np.nonzero((kept > 0) & (kept < hist))[0]]
+    pkey, pkeep = partial[-1] if partial else (-1, 0)
+    return kept, z, vmax, pkey, pkeep
+
+
+def emulate_draw_kernel(keys, kept, z, vmax, pkey, pkeep, temperature, u):
+    """sample_draw_kernel: two passes over the vocabulary in chunks of 512 × 8 consecutive entries, carries across
+    chunks for the cdf and for the rank inside the partial bin, first index with cdf ≥ u·total."""
+    V = len(keys)
+    zf = F32(z)
+    chunk = DRAW_THREADS * DRAW_ITEMS
+    vals = key_value(np.arange(65536, dtype=np.uint16))
+    with np.errstate(all="ignore"):
+        sv = (vals / F32(temperature)).astype(F32) if temperature > 0 else vals
+        e = np.exp((sv - vmax).astype(F32)).astype(F32)
+    total, pick = 0.0, -1
+    for pas in range(2):
+        carry, rank_carry, pick = 0.0, 0, -1
+        r = float(F32(u)) * total
+        for base in range(0, V, chunk):
+            p = np.zeros((DRAW_THREADS, DRAW_ITEMS), dtype=F32)
+            isp = np.zeros((DRAW_THREADS, DRAW_ITEMS), dtype=np.int64)
+            for t in range(DRAW_THREADS):
+                for j in range(DRAW_ITEMS):
+                    i = base + t * DRAW_ITEMS + j
+                    if i < V and kept[keys[i]] != 0:
+                        isp[t, j] = int(keys[i] == pkey)
+                        p[t, j] = F32(e[keys[i]] / zf)
+            n_partial = isp.sum(axis=1)
+            rank_before = np.concatenate([[0], np.cumsum(n_partial)[:-1]])
+            mine = np.zeros(DRAW_THREADS)
+            last_rank = rank_carry
+            for t in range(DRAW_THREADS):
+                rank = rank_carry + int(rank_before[t])
+                for j in range(DRAW_ITEMS):
+                    if isp[t, j]:
+                        if rank >= pkeep:
+                            p[t, j] = 0
+                        rank += 1
+                    mine[t] += float(p[t, j])
+                if t == DRAW_THREADS - 1:
+                    last_rank = rank
+            before = np.concatenate([[0.0], np.cumsum(mine)[:-1]])
+            chunk_total = float(mine.sum())
+            if pas == 1 and pick < 0:
+                cands = []
+                for t in range(DRAW_THREADS):
+                    c = carry + float(before[t])
+                    for j in range(DRAW_ITEMS):
+                        c += float(p[t, j])
+                        i = base + t * DRAW_ITEMS + j
+                        if i < V and c >= r:
+                            cands.append(i)
+                            break
+                if cands:
+                    pick = min(cands)
+            carry += chunk_total
+            rank_carry = last_rank
+            if pas == 1 and pick >= 0:
+                break
+        if pas == 0:
+            total = carry
+    if not total > 0 or pick < 0:
+        pick = V - 1 if total > 0 else 0
+    return pick
+
+
+@pytest.mark.parametrize("V,scale,cfg", [(97, 3.0, (0.8, 0, 1.0, 0.0)), (5000, 0.05, (0.6, 40, 0.95, 0.02)),
+                                         (9000, 3.0, (1.0, 7, 0.3, 0.9)), (5000, 0.05, (1.0, 50, 1.0, 0.0)),
+                                         (4097, 2.0, (0.7, 0, 0.9, 0.0)), (12000, 0.02, (1.3, 3000, 0.97, 0.001))])
+def test_thread_level_emulation_of_the_kernels(V, scale, cfg):
+    """The per-thread decomposition of sample_plan_kernel / sample_draw_kernel (bins per thread walked downwards,
+    exclusive scans over threads, chunk carries, rank inside the partial bin) gives the bin plan's result."""
+    T, k, p, mp = cfg
+    logits = _rand_bf16(V, seed=V + k, scale=scale)
+    bits = logits.view(torch.int16).numpy().view(np.uint16)
+    keys = order_key(bits)
+    hist = np.bincount(keys, minlength=65536)
+    kept_model, e_model, z_model = bins_plan(hist, T, k, p, mp)
+    kept, z, vmax, pkey, pkeep = emulate_plan_kernel(hist, V, T, k, p, mp)
+    assert np.array_equal(kept, kept_model)
+    assert abs(z - float(z_model)) <= 1e-6 * float(z_model)
+    for u in (0.0003, 0.21, 0.5, 0.77, 0.9996):
+        probs, want = bins_sample(logits, T, k, p, mp, u)
+        got = emulate_draw_kernel(keys, kept, z, vmax, pkey, pkeep, T, u)
+        if got != want:   # fp64 carries vs the model's fp32 cdf: only at a rounding boundary
+            cdf = np.cumsum(probs, dtype=F32)
+            assert probs[got] > 0 and abs(float(cdf[min(got, want)]) - u * float(cdf[-1])) < 1e-5, (u, got, want)
