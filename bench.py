@@ -211,9 +211,10 @@ def reference_cuda_baseline(spec, weights):
         prompt = torch.randint(0, spec.vocab, (PROMPT_LEN,), generator=torch.Generator().manual_seed(0)).tolist()
         with tempfile.TemporaryDirectory() as td:
             models.save_checkpoint(spec, weights, td)
-            _, _, timing = rp.run_reference(spec, td, prompt, 2, time_steps=NEW_TOKENS, timeout=180)
+            # bounded: a first-ever run of this binary on a box must not be able to stretch the bench by minutes
+            _, _, timing = rp.run_reference(spec, td, prompt, 2, time_steps=NEW_TOKENS, timeout=120)
             try:  # the same reference program with our engine behind GPTModel::model() (the TinyTorch adapter)
-                _, _, t_adapter = rp.run_reference(spec, td, prompt, 2, time_steps=NEW_TOKENS, timeout=180, b200="engine")
+                _, _, t_adapter = rp.run_reference(spec, td, prompt, 2, time_steps=NEW_TOKENS, timeout=90, b200="engine")
             except Exception as e:  # noqa: BLE001
                 t_adapter = {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
         if not timing:
