@@ -150,8 +150,16 @@ inline void registerOps() {
 class B200CausalLM : public tt::nn::Module {
  public:
   // `loaded` is the reference model after ModelLoader::load (src/huggingface/ModelLoader.cpp:25-87).
-  B200CausalLM(tt::nn::Module& loaded, const b200_model_desc& desc, tinygpt::KVCacheManager* refCache)
-      : desc_(desc), refCache_(refCache), layers_(desc.layers) {
+  // `rope` is a RoPE module built the way the model's createModel() builds each layer's (src/model/ModelLlama.h:40-43,
+  // ModelQwen2.h:34, ModelQwen3.h, ModelMistral.h): Attention keeps its own rope_ as an UNREGISTERED member
+  // (src/layer/Attention.h:61-68 registers q/k/v/o_proj only), so the table is not among namedStates(); building one
+  // more RoPE runs the reference's own op::ropeInit kernels and gives the identical fp32 table, owned here.
+  B200CausalLM(tt::nn::Module& loaded, const b200_model_desc& desc, tinygpt::KVCacheManager* refCache, tt::nn::RoPE&& rope)
+      : desc_(desc), refCache_(refCache), layers_(desc.layers), rope_(std::move(rope)) {
+    ASSERT(rope_.cache().defined() && rope_.cache().dim() == 3 && rope_.cache().shape(1) == desc.head_dim);
+    ASSERT(rope_.cache().device().type == tt::DeviceType::CUDA && rope_.cache().dtype() == tt::DType::Float32);
+    if (desc_.max_ctx > rope_.cache().shape(0)) desc_.max_ctx = (int32_t)rope_.cache().shape(0);
+    table_.rope_table = rope_.cache().dataPtr<float>();
     for (auto& [name, t] : loaded.namedStates()) {  // third_party/TinyTorch/src/Module/Module.h:43-53
       void* p = t->dataPtr<tt::BFloat16>();
       auto ends = [&](const char* s) {
@@ -160,7 +168,6 @@ class B200CausalLM : public tt::nn::Module {
       if (name == "model.embed_tokens.weight") table_.embed = p;
       else if (name == "model.norm.weight") table_.final_norm = p;
       else if (name == "lm_head.weight") table_.lm_head = p;
-      else if (ends("self_attn.rope.rope") && table_.rope_table == nullptr) table_.rope_table = t->dataPtr<float>();
       else if (name.rfind("model.layers.", 0) == 0) {
         const int l = std::stoi(name.substr(13));
         b200_layer_weights& w = layers_[l];
@@ -216,6 +223,7 @@ class B200CausalLM : public tt::nn::Module {
   b200_model_desc desc_;
   tinygpt::KVCacheManager* refCache_;
   std::vector<b200_layer_weights> layers_;
+  tt::nn::RoPE rope_;
   b200_weight_table table_{};
   std::vector<b200_engine*> engines_;
 };
@@ -223,8 +231,8 @@ class B200CausalLM : public tt::nn::Module {
 // GPTModel whose model() is the fused module; everything else is delegated to the loaded reference model.
 class ModelB200 : public tinygpt::GPTModel {
  public:
-  ModelB200(std::unique_ptr<tinygpt::GPTModel> loaded, const b200_model_desc& desc)
-      : loaded_(std::move(loaded)), fused_(loaded_->model(), desc, &kvCache_) {
+  ModelB200(std::unique_ptr<tinygpt::GPTModel> loaded, const b200_model_desc& desc, tt::nn::RoPE&& rope)
+      : loaded_(std::move(loaded)), fused_(loaded_->model(), desc, &kvCache_, std::move(rope)) {
     init();
   }
   tinygpt::GPTModelType type() override { return loaded_->type(); }

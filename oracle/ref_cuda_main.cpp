@@ -111,9 +111,9 @@ int main(int argc, char** argv) {
   }
   tt::NoGradGuard guard;
   tt::Device dev(tt::DeviceType::CUDA, 0);
-  hf::LlamaConfig llama;
-  hf::QwenConfig qwen;
-  hf::MistralConfig mistral;
+  hf::LlamaConfig llama{};
+  hf::QwenConfig qwen{};
+  hf::MistralConfig mistral{};
   std::unique_ptr<tinygpt::GPTModel> model;
   if (family == "llama") {
     fillCommon(llama, dims, eps, tie != 0);
@@ -167,7 +167,18 @@ int main(int argc, char** argv) {
     d.tp_rank = 0;
     d.tp_world = 1;
     d.tp_shard_attn = 1;
-    model = std::make_unique<b200::adapter::ModelB200>(std::move(model), d);
+    // one more RoPE, built exactly as the family's createModel() builds each layer's (ModelLlama.h:40-43 — always
+    // with a scaling config and with the ORIGINAL context when the config carries one; ModelQwen2/3.h, ModelMistral.h:
+    // no scaling, max_position_embeddings rows)
+    const tt::Options ropeOpts(dev, tt::DType::BFloat16);
+    std::optional<tt::RopeScalingConfig> scaling;
+    int64_t ropeCtx = (int64_t)dims[7];
+    if (family == "llama") {
+      scaling = tinygpt::llama::convertToRopeScalingConfig(llama);
+      ropeCtx = tinygpt::llama::getContextSize(llama);
+    }
+    tt::nn::RoPE rope((int64_t)dims[4], ropeCtx, theta, scaling, ropeOpts);
+    model = std::make_unique<b200::adapter::ModelB200>(std::move(model), d, std::move(rope));
   } else if (b200Mode != "off") {
     fprintf(stderr, "--b200 must be off, ops or engine\n");
     return 2;

@@ -426,7 +426,16 @@ int64_t attn_decode_ws_floats(int Hq, int Hkv, int hd, int nsplit) {
 }
 
 // Query heads per CTA: the whole GQA group once the context is long enough for K/V re-reads to matter, else one.
-int attn_heads_per_cta(int Hq, int Hkv, int max_ctx) { return (max_ctx > 1024) ? Hq / Hkv : 1; }
+// Only G in {1,2,3,4,7,8} is instantiated; any other group size (the reference accepts every Hq % Hkv == 0) falls back to
+// the largest instantiated divisor of the group (6 → 3, 5 → 1, 16 → 8, 12 → 4).
+int attn_heads_per_cta(int Hq, int Hkv, int max_ctx) {
+  if (max_ctx <= 1024) return 1;
+  const int group = Hq / Hkv;
+  const int built[6] = {8, 7, 4, 3, 2, 1};
+  for (int g : built)
+    if (group % g == 0) return g;
+  return 1;
+}
 
 int attn_setup_attributes() {
   static std::once_flag once;

@@ -289,13 +289,14 @@ __global__ void __launch_bounds__(kDrawThreads) sample_draw_kernel(const __nv_bf
       double before = 0.0, chunk_total = 0.0;
       ScanD(tmp.sd).ExclusiveSum(mine, before, chunk_total);
       __syncthreads();
-      if (pass == 1 && s_pick < 0) {
+      if (pass == 1) {   // no `s_pick < 0` guard: other warps may already be publishing into s_pick (atomicMin keeps the
+                         // smallest index, and the loop leaves after the first chunk that found one)
         double c = s_carry + before;
         long long found = -1;
 #pragma unroll
         for (int j = 0; j < kDrawItems; ++j) {
           c += (double)p[j];
-          if (found < 0 && i0 + j < V && c >= r) found = i0 + j;
+          if (found < 0 && i0 + j < V && p[j] > 0.f && c >= r) found = i0 + j;   // only a surviving entry can be drawn
         }
         if (found >= 0) atomicMin(reinterpret_cast<unsigned long long*>(&s_pick), (unsigned long long)found);
       }

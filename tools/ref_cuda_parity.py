@@ -104,7 +104,10 @@ def compare(name, a, b):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--models", default="tiny-qwen2,tiny-llama,tiny-qwen3,tiny-mistral,Qwen2.5-0.5B")
+    ap.add_argument("--models", default="tiny-qwen2,tiny-llama,tiny-qwen3,tiny-mistral,Qwen2.5-0.5B,Qwen3-1.7B,"
+                                        "Llama-3.2-3B,Mistral-7B-v0.3")
+    ap.add_argument("--oracle-max-params", type=float, default=4e9,
+                    help="run the CPU oracle (fp32 copies of the weights) only for models below this size")
     ap.add_argument("--new", type=int, default=24)
     ap.add_argument("--prompt", type=int, default=16)
     ap.add_argument("--json", default="")
@@ -128,18 +131,31 @@ def main():
             ref_toks_free, _, timing = run_reference(spec, td, prompt, args.new, time_steps=128 if big else 32)
         row = {"model": name, "engine_vs_reference_cuda": compare("engine-ref", logits, ref_logits)}
         # greedy ids: the reference's argmax on ITS logits, forced on our tokens, step by step
-        srt = torch.sort(ref_logits, dim=-1, descending=True).values
-        margin = (srt[:, 0] - srt[:, 1])
+        top2 = torch.topk(ref_logits, 2, dim=-1).values
+        margin = (top2[:, 0] - top2[:, 1])
+        # one bf16 ulp at the magnitude of the winning logit (8 significand bits): a margin ≤ 1 ulp is a near-tie — the
+        # two candidates are adjacent bf16 values (or equal), and any summation-order difference can swap them
+        ulp = torch.pow(2.0, torch.floor(torch.log2(top2[:, 0].abs().clamp_min(1e-30))) - 7)
+        near = margin <= ulp
         agree = (ref_toks_forced == toks)
         row["greedy_ids"] = {"equal_steps": int(agree.sum()), "steps": int(len(toks)),
+                             "near_tie_steps_margin_le_1ulp": int(near.sum()),
+                             "exact_tie_steps": int((margin == 0).sum()),
+                             "different_steps_that_are_near_ties": int((near & ~agree).sum()),
+                             "different_steps_with_decisive_margin": int((~near & ~agree).sum()),
+                             "margins_in_ulp_where_different": [round(float(m / u), 3) for m, u in
+                                                                zip(margin[~agree], ulp[~agree])],
                              "min_margin_where_different": float(margin[~agree].min()) if (~agree).any() else None,
+                             "median_margin_in_ulp": float((margin / ulp).median()),
                              "free_running_identical_prefix": int((torch.cumprod((ref_toks_free == toks).long(), 0)).sum())}
-        if not big:
+        n_params = sum(v.numel() for v in w.values())
+        if n_params <= args.oracle_max_params:
             wf = {k: v.float().cpu() for k, v in w.items()}
             _, logits_orc = orc.generate_greedy(to_oracle_cfg(spec), wf, torch.tensor(prompt), args.new,
                                                 models.rope_table(spec), "bf16", forced=toks)
             row["oracle_vs_reference_cuda"] = compare("oracle-ref", logits_orc, ref_logits)
             row["engine_vs_oracle"] = compare("engine-oracle", logits, logits_orc)
+            del wf
         row["decode_us_per_token"] = {"ours": us, "reference_cuda": timing["us_per_token"] if timing else None}
         # the drop-in boundary with the real reference around it: same program, our code behind its seams
         with tempfile.TemporaryDirectory() as td:

@@ -28,7 +28,7 @@ fi
 if want ref; then
 echo "== engine and oracle against the reference's own CUDA path (oracle/_ref/ref_cuda_decode, if it was built)"
 if [ -x oracle/_ref/ref_cuda_decode ]; then
-  timeout 1200 python tools/ref_cuda_parity.py --prefill Qwen3-1.7B:2048 --json "$OUT/ref_cuda_parity.json" > "$OUT/ref_cuda_parity.log" 2>&1
+  timeout 2400 python tools/ref_cuda_parity.py --prefill Qwen3-1.7B:2048 --json "$OUT/ref_cuda_parity.json" > "$OUT/ref_cuda_parity.log" 2>&1
   tail -n 12 "$OUT/ref_cuda_parity.log"
 else
   echo "not built: run 'make -C oracle cuda' in the container that has /root/reference"
