@@ -258,7 +258,8 @@ int64_t b200_engine_debug_trace(b200_engine* eng, uint64_t* out_host, int64_t ma
 int64_t b200_engine_position(const b200_engine* eng);
 int64_t b200_engine_launches_per_token(const b200_engine* eng);
 /* Which code paths this engine was built with (environment / defaults at create time): bit 0 CUDA graph, bit 1
- * programmatic dependent launch, bit 2 flag synchronisation, bit 3 batched GEMM prefill, bits 8-15 L2 prefetch MB. */
+ * programmatic dependent launch, bit 3 batched GEMM prefill (bit 2 and bits 8-15 belonged to variants that were measured
+ * and removed: profiles/experiments/). */
 int64_t b200_engine_options(const b200_engine* eng);
 /* Algorithmic HBM bytes one decode step reads on THIS rank at context length ctx (weights once + KV + logits). */
 int64_t b200_engine_bytes_per_token(const b200_engine* eng, int64_t ctx);

@@ -7,6 +7,11 @@
 //   ref_cuda_decode --ckpt DIR --family {llama|qwen2|qwen3|mistral} --dims H,L,Hq,Hkv,hd,I,V,ctx --theta T --eps E
 //                   --tie {0|1} [--rope-scaling f,hi,lo,orig] --ids FILE(int64) --new N [--forced FILE(int64)]
 //                   --out FILE [--time-steps K] [--b200 {off|ops|engine}] [--qkv-bias 0|1] [--qk-norm 0|1]
+//                   [--dump-rope FILE] [--batched 1]
+// --dump-rope writes the fp32 cos/sin table of a RoPE module built as the family's createModel() builds it.
+// --batched 1 (needs --forced): ONE forward over prompt + forced tokens — the reference's batched path (cuBLAS GEMM with
+// m = S + N - 1, causal TinyFA) — and the logits of the same N positions: the reference against ITSELF through two of
+// its own code paths, i.e. the summation-order noise floor of its CUDA arithmetic.
 // --b200 exercises the DROP-IN BOUNDARY with the real reference code around it (integration/tinytorch_b200_adapter.h,
 // linked against tinygpt_b200/lib/libb200decode.so):  ops    = b200::adapter::registerOps() — boundary B, the
 // reference's modules call our kernels through its own op registry;  engine = the loaded GPTModel wrapped in
@@ -85,7 +90,8 @@ int main(int argc, char** argv) {
   std::vector<double> dims, rs;
   float theta = 10000.f, eps = 1e-5f;
   int tie = 1, nNew = 8, timeSteps = 0, qkvBias = -1, qkNorm = -1;
-  std::string b200Mode = "off";
+  std::string b200Mode = "off", ropeDump;
+  int batched = 0;
   for (int i = 1; i + 1 < argc; i += 2) {
     const std::string a = argv[i];
     const char* v = argv[i + 1];
@@ -104,6 +110,8 @@ int main(int argc, char** argv) {
     else if (a == "--b200") b200Mode = v;
     else if (a == "--qkv-bias") qkvBias = atoi(v);
     else if (a == "--qk-norm") qkNorm = atoi(v);
+    else if (a == "--dump-rope") ropeDump = v;
+    else if (a == "--batched") batched = atoi(v);
   }
   if (ckpt.empty() || dims.size() != 8 || idsPath.empty() || outPath.empty()) {
     fprintf(stderr, "usage: see the header of oracle/ref_cuda_main.cpp\n");
@@ -149,6 +157,29 @@ int main(int argc, char** argv) {
   }
   model->model().to(tt::DType::BFloat16);
   model->model().eval();
+  auto makeRope = [&]() {
+    // built exactly as the family's createModel() builds each layer's (ModelLlama.h:40-43 — always with a scaling
+    // config and with the ORIGINAL context when the config carries one; ModelQwen2/3.h, ModelMistral.h: no scaling,
+    // max_position_embeddings rows)
+    const tt::Options ropeOpts(dev, tt::DType::BFloat16);
+    std::optional<tt::RopeScalingConfig> scaling;
+    int64_t ropeCtx = (int64_t)dims[7];
+    if (family == "llama") {
+      scaling = tinygpt::llama::convertToRopeScalingConfig(llama);
+      ropeCtx = tinygpt::llama::getContextSize(llama);
+    }
+    return tt::nn::RoPE((int64_t)dims[4], ropeCtx, theta, scaling, ropeOpts);
+  };
+  if (!ropeDump.empty()) {
+    tt::nn::RoPE rope = makeRope();
+    tt::Tensor t = rope.cache().to(tt::Device(tt::DeviceType::CPU));
+    FILE* rf = fopen(ropeDump.c_str(), "wb");
+    if (!rf) return 4;
+    const int64_t shp[3] = {t.shape(0), t.shape(1), t.shape(2)};
+    fwrite(shp, 8, 3, rf);
+    fwrite(t.dataPtr<float>(), 4, (size_t)t.numel(), rf);
+    fclose(rf);
+  }
   if (b200Mode == "ops") {
     b200::adapter::registerOps();           // from main(), after static initialisation
   } else if (b200Mode == "engine") {
@@ -167,17 +198,7 @@ int main(int argc, char** argv) {
     d.tp_rank = 0;
     d.tp_world = 1;
     d.tp_shard_attn = 1;
-    // one more RoPE, built exactly as the family's createModel() builds each layer's (ModelLlama.h:40-43 — always
-    // with a scaling config and with the ORIGINAL context when the config carries one; ModelQwen2/3.h, ModelMistral.h:
-    // no scaling, max_position_embeddings rows)
-    const tt::Options ropeOpts(dev, tt::DType::BFloat16);
-    std::optional<tt::RopeScalingConfig> scaling;
-    int64_t ropeCtx = (int64_t)dims[7];
-    if (family == "llama") {
-      scaling = tinygpt::llama::convertToRopeScalingConfig(llama);
-      ropeCtx = tinygpt::llama::getContextSize(llama);
-    }
-    tt::nn::RoPE rope((int64_t)dims[4], ropeCtx, theta, scaling, ropeOpts);
+    tt::nn::RoPE rope = makeRope();
     model = std::make_unique<b200::adapter::ModelB200>(std::move(model), d, std::move(rope));
   } else if (b200Mode != "off") {
     fprintf(stderr, "--b200 must be off, ops or engine\n");
@@ -210,10 +231,22 @@ int main(int argc, char** argv) {
     return tok;
   };
   model->resetCache();
-  int64_t tok = step(idsTensor(ids.data(), S), S, 0);
-  for (int k = 1; k < nNew; ++k) {
-    const int64_t in = forced.empty() ? tok : forced[k - 1];
-    tok = step(idsTensor(&in, 1), 1, k);
+  if (batched && !forced.empty()) {
+    std::vector<int64_t> all(ids);
+    all.insert(all.end(), forced.begin(), forced.begin() + (nNew - 1));
+    const int64_t n = (int64_t)all.size();
+    tt::Tensor logits = model->forward(idsTensor(all.data(), n));                  // [1, n, V] bf16
+    tt::Tensor tail = tt::function::narrow(logits, 1, S - 1, nNew).squeeze(0);     // [nNew, V]
+    tt::Tensor next = tt::function::argmax(tail, -1, true).to(tt::Device(tt::DeviceType::CPU));
+    tt::Tensor f = tail.to(tt::DType::Float32).to(tt::Device(tt::DeviceType::CPU));
+    std::memcpy(logitsAll.data(), f.dataPtr<float>(), sizeof(float) * (size_t)nNew * V);
+    for (int k = 0; k < nNew; ++k) tokens.push_back(next.dataPtr<int64_t>()[k]);
+  } else {
+    int64_t tok = step(idsTensor(ids.data(), S), S, 0);
+    for (int k = 1; k < nNew; ++k) {
+      const int64_t in = forced.empty() ? tok : forced[k - 1];
+      tok = step(idsTensor(&in, 1), 1, k);
+    }
   }
   FILE* f = fopen(outPath.c_str(), "wb");
   if (!f) return 4;

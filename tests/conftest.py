@@ -11,8 +11,6 @@ if str(ROOT) not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
-    config.addinivalue_line("markers", "staged: opt-in code paths written in a GPU-less session and not yet run on "
-                                       "hardware; skipped unless B200_STAGED=1 (see DESIGN.md §9)")
 
 
 def _has_gpu() -> bool:
@@ -24,11 +22,6 @@ def _has_gpu() -> bool:
 
 
 def pytest_collection_modifyitems(config, items):
-    if os.environ.get("B200_STAGED", "0") != "1":
-        skip_staged = pytest.mark.skip(reason="staged (not yet run on hardware): set B200_STAGED=1 to run")
-        for item in items:
-            if "staged" in item.keywords:
-                item.add_marker(skip_staged)
     if _has_gpu():
         return
     skip = pytest.mark.skip(reason="no CUDA device in this container")

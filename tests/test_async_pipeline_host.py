@@ -2,7 +2,7 @@
 rewind arithmetic) against a fake engine that plays the device's part: every enqueued step appends the next token of a
 scripted sequence to the ring exactly the way the argmax kernel does —
 ((n & 0xffffffff) << 32) | token at ring[(n - 1) % capacity] — and advances the position like b200_engine_forward /
-b200_engine_decode.  The real device path is tests/test_staged_gpu.py::test_generate_async_matches_sync_and_stops."""
+b200_engine_decode.  The real device path is tests/test_async_sampler_gpu.py::test_generate_async_matches_sync_and_stops."""
 import numpy as np
 import pytest
 

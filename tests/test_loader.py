@@ -9,7 +9,7 @@ import struct
 import pytest
 import torch
 
-from tinygpt_b200 import loader, models, tp
+from tinygpt_b200 import engine, loader, models, tp
 
 SPECS = [models.TINY_QWEN2, models.TINY_LLAMA, models.TINY_QWEN3, models.TINY_MISTRAL]
 
@@ -160,3 +160,29 @@ def test_chunked_staging_path(tmp_path, staging_bytes):
     _same(got, w)
     _, r1, _ = loader.load_checkpoint(tmp_path, device="cpu", rank=1, world=2, staging_bytes=staging_bytes)
     _same(r1, tp.shard_weights(spec, w, 1, 2))
+
+
+# --------------------------------------------------------------------------------- loader fast path, CUDA destination
+@pytest.mark.gpu
+def test_loader_cuda_staging_path(built_lib, tmp_path):
+    """The pinned-staging H2D path (chunked, strided column slices included) delivers the same bytes as the CPU path,
+    and the loaded tensors drive the engine to the same tokens as the in-memory synthetic checkpoint."""
+    from tinygpt_b200 import loader, tp
+    spec = models.TINY_QWEN2
+    w = models.synth_weights(spec, seed=9)
+    models.save_checkpoint(spec, w, str(tmp_path))
+    got_spec, got, _ = loader.load_checkpoint(tmp_path, device="cuda")
+    for k, v in w.items():
+        assert torch.equal(got[k].cpu().view(torch.int16), v.view(torch.int16)), k
+    _, r1, _ = loader.load_checkpoint(tmp_path, device="cuda", rank=1, world=2)
+    want = tp.shard_weights(spec, w, 1, 2)
+    for k, v in want.items():
+        assert torch.equal(r1[k].cpu().view(torch.int16), v.view(torch.int16)), k
+    prompt = [3, 1, 4, 1, 5, 9, 2, 6, 5]
+    a = engine.DecodeEngine(got_spec.with_ctx(128), got)
+    b = engine.DecodeEngine(spec.with_ctx(128), {k: v.to("cuda") for k, v in w.items()})
+    assert a.generate_sync(prompt, 16).tolist() == b.generate_sync(prompt, 16).tolist()
+    a.close()
+    b.close()
+
+

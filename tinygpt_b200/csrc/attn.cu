@@ -49,10 +49,7 @@ struct SplitKeys {
   static constexpr int value = (HD == 64) ? 256 : 128;
 };
 
-// FS = flag-synchronised variant (opt-in, B200_FLAGSYNC=1; common.cuh FlagSync): waits for the qkv GEMV's completion
-// counter instead of griddepcontrol.wait, reads qkv through L2, and every CTA — also one without keys — counts itself
-// done on its own counter once its last global store is issued.  FS = false is the PDL kernel unchanged.
-template <int HD, int G, bool FS>
+template <int HD, int G>
 __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnDecodeParams p) {
   constexpr int LPK = HD / 8;           // lanes per key row (16-byte pieces)
   constexpr int KPW = 32 / LPK;         // keys per warp per iteration
@@ -89,11 +86,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnDec
   const int L = pos + 1;
   const int nact = (L + CHUNK - 1) / CHUNK;
   if (split >= nact) {
-    if constexpr (FS) {
-      if (tid == 0) flag_signal(p.fs);  // nothing read, nothing written
-    } else {
-      pdl_wait();
-    }
+    pdl_wait();
     return;
   }
   const int start = split * CHUNK;
@@ -124,16 +117,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnDec
   }
 
   // qkv of this token is complete and visible from here on
-  if constexpr (FS) {
-    if (tid == 0) flag_wait(p.fs);
-    __syncthreads();
-  } else {
-    pdl_wait();
-  }
-  auto ldq = [](const __nv_bfloat16* q) -> __nv_bfloat16 {
-    if constexpr (FS) return __ldcg(q);
-    else return *q;
-  };
+  pdl_wait();
+  auto ldq = [](const __nv_bfloat16* q) -> __nv_bfloat16 { return *q; };
   if (p.trace != nullptr && hg == 0 && split == 0 && tid == 0) p.trace[1] = global_timer_ns();
 
   const int qdim = p.Hq * HD, kvdim = p.Hkv * HD;
@@ -290,13 +275,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnDec
       ws_base[((size_t)split * G + g) * (HD + 2) + d] = o;
     }
   }
-  if (nact == 1) {
-    if constexpr (FS) {
-      __syncthreads();
-      if (tid == 0) flag_signal(p.fs);
-    }
-    return;
-  }
+  if (nact == 1) return;
   if (tid < G) {
     ws_base[((size_t)split * G + tid) * (HD + 2) + HD] = ml[tid * 2];
     ws_base[((size_t)split * G + tid) * (HD + 2) + HD + 1] = ml[tid * 2 + 1];
@@ -308,12 +287,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnDec
     is_last = (t == (unsigned int)nact - 1);
   }
   __syncthreads();
-  if (!is_last) {
-    if constexpr (FS) {
-      if (tid == 0) flag_signal(p.fs);  // this CTA's partials were stored before the barrier above
-    }
-    return;
-  }
+  if (!is_last) return;
   __threadfence();
 
   // ---- merge the split partials (last CTA of this KV head)
@@ -330,30 +304,22 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnDec
     }
     p.out[(h0 + g) * HD + d] = f_to_bf16(num * (den > 0.f ? 1.f / den : 0.f));
   }
-  if constexpr (FS) __syncthreads();
-  if (tid == 0) {
-    p.tickets[hg] = 0;
-    if constexpr (FS) flag_signal(p.fs);
-  }
+  if (tid == 0) p.tickets[hg] = 0;
 }
 
 using AttnFn = void (*)(const AttnDecodeParams);
 
-template <int HD, bool FS>
-AttnFn pick_attn_fs(int G) {
+template <int HD>
+AttnFn pick_attn(int G) {
   switch (G) {
-    case 1: return attn_decode_kernel<HD, 1, FS>;
-    case 2: return attn_decode_kernel<HD, 2, FS>;
-    case 3: return attn_decode_kernel<HD, 3, FS>;
-    case 4: return attn_decode_kernel<HD, 4, FS>;
-    case 7: return attn_decode_kernel<HD, 7, FS>;
-    case 8: return attn_decode_kernel<HD, 8, FS>;
+    case 1: return attn_decode_kernel<HD, 1>;
+    case 2: return attn_decode_kernel<HD, 2>;
+    case 3: return attn_decode_kernel<HD, 3>;
+    case 4: return attn_decode_kernel<HD, 4>;
+    case 7: return attn_decode_kernel<HD, 7>;
+    case 8: return attn_decode_kernel<HD, 8>;
   }
   return nullptr;
-}
-template <int HD>
-AttnFn pick_attn(int G, bool fs = false) {
-  return fs ? pick_attn_fs<HD, true>(G) : pick_attn_fs<HD, false>(G);
 }
 
 // ------------------------------------------------------------------------------------------ general attention
@@ -443,7 +409,7 @@ int attn_setup_attributes() {
   std::call_once(once, [] {
     const int gs[6] = {1, 2, 3, 4, 7, 8};
     for (int g : gs) {
-      AttnFn fns[4] = {pick_attn<64>(g), pick_attn<128>(g), pick_attn<64>(g, true), pick_attn<128>(g, true)};
+      AttnFn fns[2] = {pick_attn<64>(g), pick_attn<128>(g)};
       for (AttnFn f : fns) {
         cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
         if (e == cudaSuccess)
@@ -470,9 +436,7 @@ int launch_attn_decode(const AttnDecodeParams& p, int hd, cudaStream_t st, bool 
   B200_CHECK_ARG(p.Hkv > 0 && p.Hq % p.Hkv == 0, "attention: Hq=%d must be a multiple of Hkv=%d", p.Hq, p.Hkv);
   const int G = p.heads_per_cta > 0 ? p.heads_per_cta : attn_heads_per_cta(p.Hq, p.Hkv, p.max_ctx);
   B200_CHECK_ARG((p.Hq / p.Hkv) % G == 0, "attention: heads per CTA %d must divide the GQA group %d", G, p.Hq / p.Hkv);
-  const bool fs = p.fs.signal_ctr != nullptr;
-  B200_CHECK_ARG(!fs || (p.fs.wait_ctr != nullptr && p.fs.epoch != nullptr), "attention: incomplete flag-sync parameters");
-  AttnFn f = (hd == 64) ? pick_attn<64>(G, fs) : pick_attn<128>(G, fs);
+  AttnFn f = (hd == 64) ? pick_attn<64>(G) : pick_attn<128>(G);
   if (!f) {
     set_error("attention: %d query heads per CTA not built (1,2,3,4,7,8 are)", G);
     return B200_ERR_UNSUPPORTED;

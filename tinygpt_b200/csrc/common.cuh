@@ -18,17 +18,13 @@ namespace b200 {
 // ---------------------------------------------------------------------------------------------------- host errors
 void set_error(const char* fmt, ...);
 
-// ------------------------------------------------------------------------------- opt-in code paths and their defaults
-// Every path that was written without a GPU at hand is chosen by one of these; the environment variable
-// overrides the default BOTH ways ("1"/"0", or the named value), so promoting a path after it has been measured is a
-// one-word change here and the variable then becomes the way to switch it off.
+// ------------------------------------------------------------------------------- selectable code paths and their defaults
+// The environment variable overrides the default BOTH ways (the named value), so a measured alternative stays one
+// variable away.  Variants that were measured and lost (flag synchronisation, register-resident small-k GEMV loop,
+// cross-kernel L2 prefetch, whole-token persistent kernel) are not here any more: profiles/experiments/.
 struct Defaults {
-  static constexpr bool kFlagSync = false;        // B200_FLAGSYNC       completion counters instead of griddepcontrol.wait
-  static constexpr bool kFlagSyncTp = false;      // B200_FLAGSYNC_TP    … also on tensor-parallel engines
-  static constexpr bool kGemvSmallK = false;      // B200_GEMV_SMALLK    register-resident small-k GEMV loop
-  static constexpr int kL2PrefetchMb = 0;         // B200_L2PF_MB        cross-kernel L2 prefetch budget (0 = off)
-  static constexpr bool kPrefillAttnMma = false;  // B200_PREFILL_ATTN   "mma" | "cuda"
-  static constexpr bool kGemmPersistent = false;  // B200_GEMM           "persistent" | "tile"
+  static constexpr bool kPrefillAttnMma = true;   // B200_PREFILL_ATTN   "mma" (tensor cores) | "cuda" (CUDA cores)
+  // B200_GEMM "persistent" | "tile": chosen per shape when unset (gemm.cu launch_gemm_bf16)
 };
 bool env_flag(const char* name, bool dflt);                       // unset → dflt; else first character == '1'
 bool env_choice(const char* name, char yes_initial, bool dflt);   // unset → dflt; else first character == yes_initial
@@ -136,50 +132,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-// ---- flag synchronisation between co-resident, PDL-launched kernels (opt-in, B200_FLAGSYNC=1; see engine.cu).
-// A kernel's CTAs count themselves "done" on a per-op counter; the dependent kernel's CTAs poll that counter instead
-// of executing griddepcontrol.wait, so they resume as soon as the LAST producer CTA has published its rows rather than
-// after the whole grid has drained and been flushed.  Counters are monotone; the target is (tokens completed + 1) ×
-// (producer CTAs), with "tokens completed" stable for the whole token (written by the last kernel of the previous one).
-struct FlagSync {
-  const unsigned long long* wait_ctr;   // producer op's completion counter, or null (= keep griddepcontrol.wait)
-  const unsigned long long* epoch;      // tokens completed by this engine
-  unsigned int wait_per_token;          // CTAs of the producer op
-  unsigned long long* signal_ctr;       // this op's completion counter
-};
-__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void red_release_gpu_add_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 __device__ __forceinline__ unsigned long long global_timer_ns();
-// ONE thread per CTA polls with acquire loads (each one a round trip to L2; the one that sees the target synchronises
-// with the producers' release-adds), the caller then releases the other threads through a CTA barrier.  A producer
-// that never arrives (a bug) traps after ~2 s instead of hanging the GPU.
-__device__ __forceinline__ void flag_wait(const FlagSync& fs) {
-  const unsigned long long target = (ld_relaxed_gpu_u64(fs.epoch) + 1ull) * (unsigned long long)fs.wait_per_token;
-  unsigned int spins = 0;
-  unsigned long long t0 = 0;
-  while (ld_acquire_gpu_u64(fs.wait_ctr) < target) {
-    if ((++spins & 0xfffu) == 0) {
-      const unsigned long long now = global_timer_ns();
-      if (t0 == 0) t0 = now;
-      if (now - t0 > 2000000000ull) __trap();
-    }
-  }
-}
-// Called by ONE thread after a CTA barrier that follows the CTA's last global store.
-__device__ __forceinline__ void flag_signal(const FlagSync& fs) { red_release_gpu_add_u64(fs.signal_ctr, 1ull); }
-// activations written by another, still-resident kernel: read through L2 (ld.global.cg), never from a stale L1 line
-__device__ __forceinline__ uint4 ld_cg_u4(const uint4* p) { return __ldcg(p); }
 
 // ---- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

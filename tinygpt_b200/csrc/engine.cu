@@ -72,8 +72,6 @@ struct b200_engine {
   unsigned long long* trace = nullptr;  // B200_TRACE=1: [launch][8] globaltimer stamps of the last token
   bool use_graph = true;
   bool use_pdl = true;
-  // opt-in (B200_FLAGSYNC=1, single GPU): kernels of a token wait on per-op completion counters instead of
-  // griddepcontrol.wait (common.cuh FlagSync).  One 128-byte line per op; fs_epoch counts completed tokens.
   // sampler (b200_engine_set_sampler): when active the last kernels of a head token are the device sampler instead of
   // the argmax; u = Philox(seed, tokens generated so far)
   bool sampler_on = false;
@@ -84,10 +82,6 @@ struct b200_engine {
   // async token pipeline (b200_engine_set_mailbox): ring in pinned host memory the argmax kernel posts tokens into
   unsigned long long* mailbox = nullptr;
   unsigned long long mailbox_cap = 1;
-  int64_t l2pf_bytes = 0;  // opt-in (B200_L2PF_MB): cross-kernel L2 prefetch budget per GEMV launch (gemv.cuh)
-  bool use_flagsync = false;
-  unsigned long long* fs_ctr = nullptr;
-  unsigned long long* fs_epoch = nullptr;
 };
 
 namespace b200 {
@@ -97,8 +91,7 @@ namespace {
 // embed: x = E[cur_tok]   (first kernel of every token)
 __global__ void __launch_bounds__(128) embed_step_kernel(__nv_bfloat16* __restrict__ x,
                                                          const __nv_bfloat16* __restrict__ table,
-                                                         const int64_t* __restrict__ tok, int64_t V, int H,
-                                                         unsigned long long* fs_signal) {
+                                                         const int64_t* __restrict__ tok, int64_t V, int H) {
   pdl_trigger();
   pdl_wait();
   int64_t id = *tok;
@@ -106,10 +99,6 @@ __global__ void __launch_bounds__(128) embed_step_kernel(__nv_bfloat16* __restri
   const uint4* s4 = reinterpret_cast<const uint4*>(table + id * H);
   uint4* d4 = reinterpret_cast<uint4*>(x);
   for (int i = threadIdx.x; i < (H >> 3); i += blockDim.x) d4[i] = s4[i];
-  if (fs_signal != nullptr) {  // flag-sync engines: the first op of the token counts itself done
-    __syncthreads();
-    if (threadIdx.x == 0) red_release_gpu_add_u64(fs_signal, 1ull);
-  }
 }
 
 // Tensor parallel: last kernel of a token.  With a head: wait for every rank's (max logit, global index) candidate,
@@ -124,7 +113,6 @@ struct TpFinish {
   int gen_cap;
   int world;
   int with_head;
-  unsigned long long* fs_epoch_inc;  // flag-sync engines: tokens completed (this node has a full dependency)
 };
 __global__ void tp_finish_kernel(const TpFinish f) {
   pdl_trigger();
@@ -164,7 +152,6 @@ __global__ void tp_finish_kernel(const TpFinish f) {
   }
   *f.pos += 1;
   *f.epoch = ep + 1;
-  if (f.fs_epoch_inc != nullptr) *f.fs_epoch_inc += 1ull;
 }
 
 }  // namespace
@@ -187,35 +174,14 @@ static int engine_launch_token(b200_engine* e, cudaStream_t st, bool with_head) 
   // NOTE (measured on B200, CUDA 12.9 / driver 580): when the LAST kernel node of a captured graph has a programmatic
   // (PDL) incoming edge, work enqueued after the graph launch can start before that node has finished.  The last
   // launch of each graph therefore uses a normal full dependency, and so does the first (it has no upstream).
-  // flag-sync bookkeeping: op index → counter line; every launch waits on its predecessor's line and signals its own
-  const bool fs = e->use_flagsync;
-  int fs_op = 0;
-  unsigned int fs_prev_ctas = 1;
-  auto fs_line = [&](int op) { return e->fs_ctr + (size_t)op * 16; };
-  auto fs_next = [&](unsigned int my_ctas) {  // FlagSync of the next launch in program order
-    FlagSync f{};
-    if (fs) {
-      f.wait_ctr = fs_line(fs_op);
-      f.epoch = e->fs_epoch;
-      f.wait_per_token = fs_prev_ctas;
-      f.signal_ctr = fs_line(++fs_op);
-      fs_prev_ctas = my_ctas;
-    }
-    return f;
-  };
   B200_CUDA(launch_pdl(embed_step_kernel, dim3(1), dim3(128), 0, st, false, e->x, e->embed, (const int64_t*)e->cur_tok,
-                       (int64_t)d.vocab, (int)d.hidden, fs ? fs_line(0) : (unsigned long long*)nullptr));
-  const unsigned int attn_ctas =
-      (unsigned int)(e->nsplit * (e->Hq_l / attn_heads_per_cta(e->Hq_l, e->Hkv_l, d.max_ctx)));
+                       (int64_t)d.vocab, (int)d.hidden));
   const size_t kv_layer = (size_t)d.max_ctx * e->Hkv_l * d.head_dim;
   int slot = 0;
   auto tr = [&]() -> unsigned long long* { return e->trace ? e->trace + 8 * (slot++) : nullptr; };
-  const bool pf = e->l2pf_bytes > 0;
   for (int l = 0; l < d.layers; ++l) {
     GemvPlan q = e->p_qkv[l];
-    if (pf) gemv_plan_prefetch(&q, e->p_o[l], e->l2pf_bytes);
     q.p.trace = tr();
-    q.p.fs = fs_next((unsigned int)q.grid);
     if ((rc = gemv_launch(q, st, pdl)) != B200_OK) return rc;
     AttnDecodeParams a{};
     a.trace = tr();
@@ -235,41 +201,22 @@ static int engine_launch_token(b200_engine* e, cudaStream_t st, bool with_head) 
     a.Hkv = e->Hkv_l;
     a.nsplit = e->nsplit;
     a.max_ctx = d.max_ctx;
-    a.fs = fs_next(attn_ctas);
     if ((rc = launch_attn_decode(a, d.head_dim, st, pdl)) != B200_OK) return rc;
     GemvPlan o = e->p_o[l], gu = e->p_gu[l];
     o.p.trace = tr();
     gu.p.trace = tr();
-    if (pf) {
-      gemv_plan_prefetch(&o, e->p_gu[l], e->l2pf_bytes);
-      gemv_plan_prefetch(&gu, e->p_down[l], e->l2pf_bytes);
-    }
-    o.p.fs = fs_next((unsigned int)o.grid);
     if ((rc = gemv_launch(o, st, pdl)) != B200_OK) return rc;
-    gu.p.fs = fs_next((unsigned int)gu.grid);
     if ((rc = gemv_launch(gu, st, pdl)) != B200_OK) return rc;
     const bool last_node = !with_head && l == d.layers - 1;
     GemvPlan dn = e->p_down[l];
     const bool tp = e->tp_world > 1;
     dn.p.pos_inc = (last_node && !tp) ? e->pos : nullptr;  // the LAST kernel of a token advances the position
     dn.p.trace = tr();
-    if (pf) {
-      if (l + 1 < d.layers) gemv_plan_prefetch(&dn, e->p_qkv[l + 1], e->l2pf_bytes);
-      else if (with_head) gemv_plan_prefetch(&dn, e->p_head, e->l2pf_bytes);
-    }
-    dn.p.fs = fs_next((unsigned int)dn.grid);
-    if (fs && last_node && !tp) {  // full dependency instead of a poll; the only place a body-only token advances the
-                                   // epoch (tensor parallel: tp_finish_kernel is the last node and does it)
-      dn.p.fs.wait_ctr = nullptr;
-      dn.p.epoch_inc = e->fs_epoch;
-    }
     if ((rc = gemv_launch(dn, st, pdl && !(last_node && !tp))) != B200_OK) return rc;
   }
   if (with_head) {
     GemvPlan hd = e->p_head;
     hd.p.trace = tr();
-    if (pf) gemv_plan_prefetch(&hd, e->p_qkv[0], e->l2pf_bytes);  // the next token starts there
-    hd.p.fs = fs_next((unsigned int)hd.grid);
     if ((rc = gemv_launch(hd, st, pdl)) != B200_OK) return rc;
     int64_t* amax = reinterpret_cast<int64_t*>((uint8_t*)e->argmax_ws + argmax_workspace_bytes(1, e->V_l));
     ArgmaxPublish pub;
@@ -279,7 +226,6 @@ static int engine_launch_token(b200_engine* e, cudaStream_t st, bool with_head) 
       pub.gen_log = e->gen_log;
       pub.gen_count = e->gen_count;
       pub.gen_cap = e->gen_cap;
-      pub.epoch_inc = fs ? e->fs_epoch : nullptr;  // full dependency on the lm_head: every CTA of the token is done
       pub.mailbox = e->mailbox;
       pub.mailbox_cap = e->mailbox_cap;
       if (e->sampler_on) {
@@ -309,7 +255,6 @@ static int engine_launch_token(b200_engine* e, cudaStream_t st, bool with_head) 
     f.gen_cap = e->gen_cap;
     f.world = e->tp_world;
     f.with_head = with_head ? 1 : 0;
-    f.fs_epoch_inc = fs ? e->fs_epoch : nullptr;
     B200_CUDA(launch_pdl(tp_finish_kernel, dim3(1), dim3(32), 0, st, false, f));  // last node: full dependency
   }
   return B200_OK;
@@ -430,11 +375,6 @@ static int engine_build(const b200_model_desc* desc, const b200_weight_table* w,
   e->use_graph = !(env && env[0] == '1');
   env = std::getenv("B200_NO_PDL");
   e->use_pdl = !(env && env[0] == '1');
-  // tensor-parallel engines take flag-sync only when asked twice (B200_FLAGSYNC=1 B200_FLAGSYNC_TP=1): validate on one
-  // GPU first
-  e->use_flagsync = env_flag("B200_FLAGSYNC", Defaults::kFlagSync) && e->use_pdl &&
-                    (world == 1 || env_flag("B200_FLAGSYNC_TP", Defaults::kFlagSyncTp));
-  e->l2pf_bytes = (int64_t)env_int("B200_L2PF_MB", Defaults::kL2PrefetchMb, 0, 64) << 20;
   env = std::getenv("B200_NO_PREFILL_GEMM");
   e->use_prefill_gemm = !(env && env[0] == '1');
   e->final_norm_w = w->final_norm;
@@ -477,8 +417,6 @@ static int engine_build(const b200_model_desc* desc, const b200_weight_table* w,
   const size_t o_pos = take(16);
   const size_t o_cnt = take(8);
   const size_t o_epoch = take(16);
-  const size_t o_fsctr = take((size_t)(5 * d.layers + 3) * 128);
-  const size_t o_fsepoch = take(16);
   const size_t o_sample = take((size_t)sample_workspace_bytes());
   e->arena_bytes = off;
   B200_CUDA(cudaMalloc((void**)&e->arena, e->arena_bytes));
@@ -500,8 +438,6 @@ static int engine_build(const b200_model_desc* desc, const b200_weight_table* w,
   e->gen_log = (int64_t*)(e->arena + o_log);
   e->pos = (int*)(e->arena + o_pos);
   e->gen_count = (unsigned long long*)(e->arena + o_cnt);
-  e->fs_ctr = (unsigned long long*)(e->arena + o_fsctr);
-  e->fs_epoch = (unsigned long long*)(e->arena + o_fsepoch);
   e->sample_ws = (void*)(e->arena + o_sample);
 
   // ---- shared-memory budgets.  PDL keeps two consecutive kernels resident on an SM, and a kernel's TMA ring is
@@ -630,7 +566,7 @@ static int engine_build(const b200_model_desc* desc, const b200_weight_table* w,
 // points kept by running bias / residual / SiLU·mul / norms as the separate ops they are in the reference
 // [ref: src/model/GPTModel.h:51-58; src/layer/Attention.h:71-112; src/layer/GatedMLP.h:37-41].  K/V rows of all S
 // tokens are written in place; the lm_head runs for the LAST position only (GPTEngine::genNextToken narrows to it).
-static constexpr int kPrefillChunk = 512;
+static constexpr int kPrefillChunk = 2048;
 static constexpr int kPrefillMin = 8;
 
 static int prefill_workspace(b200_engine* e, int chunk) {
@@ -699,7 +635,8 @@ static int prefill_chunk(b200_engine* e, const int64_t* ids, int S, int p0, bool
 // whole prompt through the GEMM path, then lm_head + argmax for the last position
 static int engine_prefill(b200_engine* e, const int64_t* ids, int64_t S, cudaStream_t st) {
   int rc;
-  // tokens per pass through the layers: B200_PREFILL_CHUNK (multiple of 128, 128 … 8192) overrides the default — bigger
+  // tokens per pass through the layers (default 2048: measured 22.1 → 14.3 ms for config 4 against chunks of 512):
+  // B200_PREFILL_CHUNK (multiple of 128, 128 … 8192) overrides — bigger
   // chunks give the o_proj / down_proj GEMMs more than 64 tiles for 148 SMs at the price of a bigger workspace
   int chunk = kPrefillChunk;
   if (const char* env = std::getenv("B200_PREFILL_CHUNK")) {
@@ -927,8 +864,7 @@ int64_t b200_engine_debug_trace(b200_engine* e, uint64_t* out_host, int64_t max_
 int64_t b200_engine_launches_per_token(const b200_engine* e) { return e ? e->launches_per_token : -1; }
 int64_t b200_engine_options(const b200_engine* e) {
   if (!e) return -1;
-  return (e->use_graph ? 1 : 0) | (e->use_pdl ? 2 : 0) | (e->use_flagsync ? 4 : 0) | (e->use_prefill_gemm ? 8 : 0) |
-         ((e->l2pf_bytes >> 20) << 8);
+  return (e->use_graph ? 1 : 0) | (e->use_pdl ? 2 : 0) | (e->use_prefill_gemm ? 8 : 0);
 }
 
 int64_t b200_engine_bytes_per_token(const b200_engine* e, int64_t ctx) {

@@ -188,8 +188,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------------ persistent variant
-// Opt-in (B200_GEMM=persistent) until it has run against the oracle on hardware.  Same roles and the same verified
-// descriptors / TMEM access shapes as gemm_tcgen05_kernel, re-arranged for throughput:
+// The kernel for shapes whose tiles fill the GPU (launch_gemm_bf16 chooses; tests/test_prefill_gpu.py: bit-identical to
+// the 128 × 128 kernel on ≥ 99.9 % of the elements, ≤ 1 ulp against the oracle).  Same roles and the same descriptors /
+// TMEM access shapes as gemm_tcgen05_kernel, re-arranged for throughput:
 //   * 128 × 256 output tiles (one tcgen05.mma is M128 N256 K16): per 64-wide k-block the MMA pipe is busy 512 cycles
 //     and reads 48 KB of shared memory (96 B/clk; the 128 × 128 tile sits exactly on the 128 B/clk limit),
 //   * persistent CTAs (grid = min(tiles, #SMs)) walking tiles m-fastest, so concurrently running CTAs share weight rows
@@ -400,7 +401,11 @@ int launch_gemm_bf16(void* C, const void* A, const void* B, int64_t M, int64_t N
   }
   CUtensorMap ta, tb;
   int rc;
-  if (env_choice("B200_GEMM", 'p', Defaults::kGemmPersistent)) {  // "persistent" | "tile", see the persistent kernel
+  // Which kernel: the persistent 128×256 one when its tiles fill the GPU (measured on B200, tools/gemm_bench.py: 0.55–0.74
+  // of the cuBLAS bf16 peak at M = 2048 against 0.39–0.49 for one 128×128 tile per CTA; with fewer than ~100 tiles the
+  // small-tile kernel wins).  B200_GEMM = "persistent" | "tile" forces either.
+  const int64_t ptiles = ((M + kBM - 1) / kBM) * ((N + kPBN - 1) / kPBN);
+  if (env_choice("B200_GEMM", 'p', ptiles >= 100)) {
     static std::once_flag p_once;
     static cudaError_t p_err = cudaSuccess;
     static int sms = 0;

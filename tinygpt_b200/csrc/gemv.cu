@@ -51,21 +51,9 @@ __device__ __forceinline__ void st_volatile_u2(uint2* p, const uint2 v) {
   asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
 }
 
-// FS = flag-synchronised variant (opt-in, B200_FLAGSYNC=1): the dependency on the producer kernel is a completion
-// counter polled by one thread (common.cuh FlagSync) instead of griddepcontrol.wait, activations are read through L2
-// (ld.global.cg) and the CTA counts itself done at the end.  FS = false compiles to the PDL kernel unchanged.
-// SMALLK = opt-in consumer loop (B200_GEMV_SMALLK=1) for the latency-bound small-k matrices (k_pad ≤ 1024, RPW 1, at
-// most kSmallkMaxRb row blocks per CTA: Qwen2.5-0.5B's qkv / o_proj / gate|up).  When the dependency resolves, all of
-// the CTA's weights already sit in the ring, so the job is to drain shared memory as fast as possible: the activation
-// vector lives in REGISTERS (32 fp32 per lane, read from shared memory once instead of once per row block and warp),
-// all row blocks are accumulated before any reduction, the xor-shuffle trees of all rows are interleaved, and lane j
-// finishes row block j so that the epilogues (SiLU, residual, store) of all row blocks run side by side.  The FMAs of a
-// row are issued in exactly the order of the default loop ⇒ bit-identical results.
-constexpr int kSmallkMaxRb = 6;
-template <int RPW, int NSEG, int PRO, int EPI, bool FS, bool SMALLK = false>
+template <int RPW, int NSEG, int PRO, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
-gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap,
-                   const __grid_constant__ CUtensorMap pf_tmap) {
+gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap) {
   constexpr int kBoxR = kNW * RPW;
   constexpr int KB = kboxes(RPW, NSEG);                 // 256-column boxes per stage (stage = 16 KB, 32 KB for 4×2)
   constexpr int kBoxBytes = kBoxR * kRowBytes;
@@ -118,28 +106,6 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap,
           }
         }
       }
-      // cross-kernel L2 prefetch (opt-in, gemv.cuh): queued behind this CTA's own last loads.  This CTA covers the
-      // next kernel's CTAs c ≡ blockIdx.x (mod gridDim.x), stage t of CTA c = (row block c + (t / ksteps)·grid, k step
-      // t % ksteps), exactly the boxes that kernel's producer will ask for once its ring slots free up.
-      if (p.pf_count != 0) {
-#pragma unroll 1
-        for (int c = (int)blockIdx.x; c < p.pf_grid; c += (int)gridDim.x) {
-#pragma unroll 1
-          for (int t = p.pf_begin; t < p.pf_begin + p.pf_count; ++t) {
-            const int rb = c + (t / p.pf_ksteps) * p.pf_grid;
-            if (rb >= p.pf_rowblocks) break;
-            const int ks = t % p.pf_ksteps;
-#pragma unroll 1
-            for (int kb = 0; kb < p.pf_kb; ++kb)
-#pragma unroll 1
-              for (int seg = 0; seg < p.pf_nseg; ++seg)
-                asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(
-                                 reinterpret_cast<uint64_t>(&pf_tmap)),
-                             "r"((ks * p.pf_kb + kb) * kBoxK), "r"(seg * p.pf_seg_rows + rb * p.pf_box_r)
-                             : "memory");
-          }
-        }
-      }
     }
     return;
   }
@@ -167,20 +133,8 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap,
   }
 
   // the producer kernel's output (x, residual) is complete and visible from here on
-  if constexpr (FS) {
-    if (p.fs.wait_ctr != nullptr) {
-      if (ctid == 0) flag_wait(p.fs);
-      named_bar_sync(1, kConsumers);
-    } else {
-      pdl_wait();  // node with a full dependency (last kernel of a graph): nothing to poll
-    }
-  } else {
-    pdl_wait();
-  }
-  auto ldx = [](const uint4* q) -> uint4 {
-    if constexpr (FS) return ld_cg_u4(q);
-    else return *q;
-  };
+  pdl_wait();
+  auto ldx = [](const uint4* q) -> uint4 { return *q; };
   unsigned int tp_tag = 0;
   if constexpr (EPI == EPI_TP_PUSH) tp_tag = (unsigned int)(*p.tp_epoch + 1ull);
   if (p.trace != nullptr && blockIdx.x == 0 && ctid == 0) p.trace[1] = global_timer_ns();
@@ -231,9 +185,7 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap,
             a.z += __uint_as_float(w1[r].x);
             a.w += __uint_as_float(w1[r].z);
           }
-        uint2 rr;  // hidden state stored by CTA 0 of an earlier, possibly still resident kernel: through L2 under FS
-        if constexpr (FS) rr = __ldcg(reinterpret_cast<const uint2*>(p.tp_residual + 4 * i));
-        else rr = *reinterpret_cast<const uint2*>(p.tp_residual + 4 * i);
+        const uint2 rr = *reinterpret_cast<const uint2*>(p.tp_residual + 4 * i);
         const __nv_bfloat162 r01 = *reinterpret_cast<const __nv_bfloat162*>(&rr.x);
         const __nv_bfloat162 r23 = *reinterpret_cast<const __nv_bfloat162*>(&rr.y);
         const __nv_bfloat162 h01 = __hadd2(r01, __floats2bfloat162_rn(a.x, a.y));
@@ -314,109 +266,12 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap,
   int s = 0;
   uint32_t ph = 0;
   const uint8_t* const my_rows = stage_base + (size_t)(warp * RPW) * kRowBytes + lane * 16;
-  if constexpr (SMALLK) {
-    static_assert(RPW == 1 && (EPI == EPI_PLAIN || EPI == EPI_RESIDUAL || EPI == EPI_SILU_MUL), "SMALLK: RPW 1 only");
-    constexpr int kMaxBox = 4;               // k_pad ≤ 1024
-    constexpr int kKsMax = kMaxBox / KB;     // k steps per row block at most
-    float xf[kMaxBox][8];
-#pragma unroll
-    for (int b = 0; b < kMaxBox; ++b) {
-      if (b * kBoxK < p.k_pad) {
-        unpack8(*reinterpret_cast<const uint4*>(xs + b * kBoxK + lane * 8), xf[b]);
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) xf[b][e] = 0.f;
-      }
-    }
-    // lane j finishes row block j of this CTA: its epilogue operand is requested before the k loops
-    const int my_row = ((int)blockIdx.x + lane * (int)gridDim.x) * kBoxR + warp;
-    const bool my_valid = lane < my_rbs && my_row < p.n;
-    __nv_bfloat16 res_v = f_to_bf16(0.f);
-    if constexpr (EPI == EPI_RESIDUAL) {
-      if (my_valid) {
-        if constexpr (FS) res_v = __ldcg(p.residual + my_row);
-        else res_v = p.residual[my_row];
-      }
-    }
-    if constexpr (EPI == EPI_PLAIN) {
-      if (p.bias != nullptr && my_valid) bias_v = p.bias[my_row];
-    }
-    float acc[kSmallkMaxRb][NSEG], acc_b[kSmallkMaxRb][NSEG];
-#pragma unroll
-    for (int i = 0; i < kSmallkMaxRb; ++i)
-#pragma unroll
-      for (int seg = 0; seg < NSEG; ++seg) acc[i][seg] = acc_b[i][seg] = 0.f;
-#pragma unroll
-    for (int i = 0; i < kSmallkMaxRb; ++i) {
-      if (i < my_rbs) {
-#pragma unroll
-        for (int ks = 0; ks < kKsMax; ++ks) {
-          if (ks < ksteps) {
-            mbar_wait(&full[s], ph);
-            const uint8_t* st = my_rows + (size_t)s * kStageBytes;
-            uint4 wv[KB][NSEG];
-#pragma unroll
-            for (int kb = 0; kb < KB; ++kb)
-#pragma unroll
-              for (int seg = 0; seg < NSEG; ++seg)
-                wv[kb][seg] = *reinterpret_cast<const uint4*>(st + (kb * NSEG + seg) * kBoxBytes);
-#pragma unroll
-            for (int kb = 0; kb < KB; ++kb)
-#pragma unroll
-              for (int seg = 0; seg < NSEG; ++seg) dot8x2(wv[kb][seg], xf[ks * KB + kb], acc[i][seg], acc_b[i][seg]);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
-            if (++s == p.stages) {
-              s = 0;
-              ph ^= 1;
-            }
-          }
-        }
-      }
-    }
-    // all rows reduced together: independent shuffle chains interleave
-#pragma unroll
-    for (int i = 0; i < kSmallkMaxRb; ++i)
-#pragma unroll
-      for (int seg = 0; seg < NSEG; ++seg) acc[i][seg] += acc_b[i][seg];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-      for (int i = 0; i < kSmallkMaxRb; ++i)
-#pragma unroll
-        for (int seg = 0; seg < NSEG; ++seg) acc[i][seg] += __shfl_xor_sync(0xffffffffu, acc[i][seg], o);
-    float a0 = acc[0][0], a1 = acc[0][NSEG - 1];
-#pragma unroll
-    for (int j = 1; j < kSmallkMaxRb; ++j) {
-      if (lane == j) {
-        a0 = acc[j][0];
-        a1 = acc[j][NSEG - 1];
-      }
-    }
-    if (my_valid) {
-      if constexpr (EPI == EPI_PLAIN) {
-        __nv_bfloat16 v = f_to_bf16(a0);
-        if (p.bias != nullptr) v = __hadd(v, bias_v);
-        p.y[my_row] = v;
-      } else if constexpr (EPI == EPI_RESIDUAL) {
-        p.y[my_row] = __hadd(res_v, f_to_bf16(a0));
-      } else {  // EPI_SILU_MUL
-        const float g = round_bf16(a0);
-        const __nv_bfloat16 sg = f_to_bf16(g / (1.f + expf(-g)));
-        p.y[my_row] = __hmul(sg, f_to_bf16(a1));
-      }
-    }
-  }
-  const int loop_rbs = SMALLK ? 0 : my_rbs;  // the default loop below; SMALLK has done everything above
-  for (int i = 0; i < loop_rbs; ++i) {
+  for (int i = 0; i < my_rbs; ++i) {
     const int row_base = ((int)blockIdx.x + i * (int)gridDim.x) * kBoxR + warp * RPW;
     // operands of the epilogue are requested now so that their latency hides behind the k loop
     __nv_bfloat16 res_v = f_to_bf16(0.f);
     if constexpr (EPI == EPI_RESIDUAL) {
-      if (lane < RPW && row_base + lane < p.n) {
-        if constexpr (FS) res_v = __ldcg(p.residual + row_base + lane);
-        else res_v = p.residual[row_base + lane];
-      }
+      if (lane < RPW && row_base + lane < p.n) res_v = p.residual[row_base + lane];
     }
     if constexpr (EPI == EPI_PLAIN) {
       if (i > 0 && p.bias != nullptr && lane < RPW && row_base + lane < p.n) bias_v = p.bias[row_base + lane];
@@ -494,60 +349,26 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap,
   }
 
   if (p.pos_inc != nullptr && blockIdx.x == 0 && ctid == 0) *p.pos_inc += 1;
-  if constexpr (FS) {
-    // every consumer's rows are stored → one release-add publishes the CTA.  The token counter is advanced only by a
-    // node with a full dependency (fs.wait_ctr == null), i.e. when no CTA of the token still has to read it.
-    named_bar_sync(1, kConsumers);
-    if (ctid == 0) {
-      if (p.epoch_inc != nullptr && blockIdx.x == 0) *p.epoch_inc += 1ull;
-      if (p.fs.signal_ctr != nullptr) flag_signal(p.fs);
-    }
-  }
   if (p.trace != nullptr && blockIdx.x == 0 && ctid == 0) p.trace[2] = global_timer_ns();
 
 }
 
 // ------------------------------------------------------------------------------------------------------ dispatch
-using KernelFn = void (*)(const GemvParams, const CUtensorMap, const CUtensorMap);
-
-// SMALLK instantiations: RPW 1, the single-GPU engine's three k = H launches
-KernelFn pick_smallk(int nseg, int pro, int epi, bool fs) {
-#define B200_SK(N, P, E)                                                                       \
-  if (nseg == N && pro == P && epi == E)                                                       \
-    return fs ? gemv_stream_kernel<1, N, P, E, true, true> : gemv_stream_kernel<1, N, P, E, false, true>;
-  B200_SK(1, PRO_RMSNORM, EPI_PLAIN)
-  B200_SK(1, PRO_PLAIN, EPI_RESIDUAL)
-  B200_SK(2, PRO_RMSNORM, EPI_SILU_MUL)
-#undef B200_SK
-  return nullptr;
-}
+using KernelFn = void (*)(const GemvParams, const CUtensorMap);
 
 template <int RPW>
-KernelFn pick_kernel(int nseg, int pro, int epi, bool fs) {
-  if (fs) {  // the engine's four launches per layer + lm_head, single GPU and tensor parallel
-    if (nseg == 2) {
-      if (epi != EPI_SILU_MUL) return nullptr;
-      if (pro == PRO_RMSNORM) return gemv_stream_kernel<RPW, 2, PRO_RMSNORM, EPI_SILU_MUL, true>;
-      if (pro == PRO_TP_RMSNORM) return gemv_stream_kernel<RPW, 2, PRO_TP_RMSNORM, EPI_SILU_MUL, true>;
-      return nullptr;
-    }
-    if (pro == PRO_RMSNORM && epi == EPI_PLAIN) return gemv_stream_kernel<RPW, 1, PRO_RMSNORM, EPI_PLAIN, true>;
-    if (pro == PRO_PLAIN && epi == EPI_RESIDUAL) return gemv_stream_kernel<RPW, 1, PRO_PLAIN, EPI_RESIDUAL, true>;
-    if (pro == PRO_TP_RMSNORM && epi == EPI_PLAIN) return gemv_stream_kernel<RPW, 1, PRO_TP_RMSNORM, EPI_PLAIN, true>;
-    if (pro == PRO_PLAIN && epi == EPI_TP_PUSH) return gemv_stream_kernel<RPW, 1, PRO_PLAIN, EPI_TP_PUSH, true>;
-    return nullptr;
-  }
+KernelFn pick_kernel(int nseg, int pro, int epi) {
   if (nseg == 2) {
     if (epi != EPI_SILU_MUL) return nullptr;
     switch (pro) {
-      case PRO_PLAIN: return gemv_stream_kernel<RPW, 2, PRO_PLAIN, EPI_SILU_MUL, false>;
-      case PRO_RMSNORM: return gemv_stream_kernel<RPW, 2, PRO_RMSNORM, EPI_SILU_MUL, false>;
-      case PRO_TP_RMSNORM: return gemv_stream_kernel<RPW, 2, PRO_TP_RMSNORM, EPI_SILU_MUL, false>;
+      case PRO_PLAIN: return gemv_stream_kernel<RPW, 2, PRO_PLAIN, EPI_SILU_MUL>;
+      case PRO_RMSNORM: return gemv_stream_kernel<RPW, 2, PRO_RMSNORM, EPI_SILU_MUL>;
+      case PRO_TP_RMSNORM: return gemv_stream_kernel<RPW, 2, PRO_TP_RMSNORM, EPI_SILU_MUL>;
     }
     return nullptr;
   }
 #define B200_PICK(P, E) \
-  if (pro == P && epi == E) return gemv_stream_kernel<RPW, 1, P, E, false>;
+  if (pro == P && epi == E) return gemv_stream_kernel<RPW, 1, P, E>;
   B200_PICK(PRO_PLAIN, EPI_PLAIN)
   B200_PICK(PRO_PLAIN, EPI_RESIDUAL)
   B200_PICK(PRO_PLAIN, EPI_TP_PUSH)
@@ -557,12 +378,11 @@ KernelFn pick_kernel(int nseg, int pro, int epi, bool fs) {
   return nullptr;
 }
 
-KernelFn pick(int rpw, int nseg, int pro, int epi, bool fs = false, bool smallk = false) {
-  if (smallk) return rpw == 1 ? pick_smallk(nseg, pro, epi, fs) : nullptr;
+KernelFn pick(int rpw, int nseg, int pro, int epi) {
   switch (rpw) {
-    case 1: return pick_kernel<1>(nseg, pro, epi, fs);
-    case 2: return pick_kernel<2>(nseg, pro, epi, fs);
-    case 4: return pick_kernel<4>(nseg, pro, epi, fs);
+    case 1: return pick_kernel<1>(nseg, pro, epi);
+    case 2: return pick_kernel<2>(nseg, pro, epi);
+    case 4: return pick_kernel<4>(nseg, pro, epi);
   }
   return nullptr;
 }
@@ -577,9 +397,8 @@ int gemv_setup_attributes() {
     for (int rpw : rpws)
       for (int nseg = 1; nseg <= 2; ++nseg)
         for (int pro = 0; pro < 3; ++pro)
-          for (int epi = 0; epi < 4; ++epi)
-            for (int fs = 0; fs < 4; ++fs) {
-            KernelFn f = pick(rpw, nseg, pro, epi, (fs & 1) != 0, (fs & 2) != 0);
+          for (int epi = 0; epi < 4; ++epi) {
+            KernelFn f = pick(rpw, nseg, pro, epi);
             if (!f) continue;
             cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemvMaxSmem + 4096);
             // one carveout for every kernel of the token: a change of carveout between launches drains the SM and
@@ -674,51 +493,19 @@ int gemv_make_plan(GemvPlan* plan, const void* W, int64_t rows_total, int64_t n,
   plan->p.rowblocks = (int)sh.rbs;
   plan->p.stages = stages;
   plan->p.tp_world = 1;
-  // opt-in register-resident small-k consumer loop (see gemv_stream_kernel SMALLK)
-  plan->smallk = env_flag("B200_GEMV_SMALLK", Defaults::kGemvSmallK) && sh.rpw == 1 && sh.k_pad <= 1024 && ctas_per_sm == 1 &&
-                 (sh.rbs + g - 1) / g <= kSmallkMaxRb && pick_smallk(nseg, pro, epi, false) != nullptr;
   B200_CHECK_ARG(pick(sh.rpw, nseg, pro, epi) != nullptr, "gemv: no kernel for nseg=%d pro=%d epi=%d", nseg, pro, epi);
   B200_CHECK_ARG(plan->smem <= kGemvMaxSmem + 4096, "gemv: k=%lld needs %d bytes of shared memory", (long long)k,
                  plan->smem);
-  const int trc = make_tmap_2d_bf16(&plan->tmap, W, rows_total, k, sh.box_r, kBoxK);
-  plan->pf_tmap = plan->tmap;  // a valid descriptor even when nothing is prefetched
-  return trc;
-}
-
-void gemv_plan_prefetch(GemvPlan* cur, const GemvPlan& next, int64_t budget_bytes) {
-  cur->p.pf_count = 0;
-  if (budget_bytes <= 0 || cur->grid <= 0 || next.grid <= 0) return;
-  const int kb = kboxes(next.rpw, next.nseg);
-  const int ksteps = next.p.k_pad / (kBoxK * kb);
-  const int64_t stage_bytes = (int64_t)kb * next.nseg * 8 * next.rpw * kRowBytes;
-  const int64_t rbs_per_cta = (next.p.rowblocks + next.grid - 1) / next.grid;
-  const int64_t total_stages = rbs_per_cta * ksteps;                      // of next's busiest CTA
-  const int64_t begin = next.p.stages;                                    // its ring holds stages [0, stages)
-  int64_t count = budget_bytes / (stage_bytes * next.grid);
-  count = std::min<int64_t>(count, total_stages - begin);
-  if (count <= 0) return;
-  cur->pf_tmap = next.tmap;
-  cur->p.pf_begin = (int)begin;
-  cur->p.pf_count = (int)count;
-  cur->p.pf_grid = next.grid;
-  cur->p.pf_rowblocks = next.p.rowblocks;
-  cur->p.pf_ksteps = ksteps;
-  cur->p.pf_kb = kb;
-  cur->p.pf_nseg = next.nseg;
-  cur->p.pf_box_r = 8 * next.rpw;
-  cur->p.pf_seg_rows = next.p.seg_rows;
+  return make_tmap_2d_bf16(&plan->tmap, W, rows_total, k, sh.box_r, kBoxK);
 }
 
 int gemv_launch(const GemvPlan& plan, cudaStream_t stream, bool pdl) {
-  const bool fs = plan.p.fs.signal_ctr != nullptr || plan.p.fs.wait_ctr != nullptr;
-  KernelFn f = plan.smallk ? pick(plan.rpw, plan.nseg, plan.pro, plan.epi, fs, true) : nullptr;
-  if (!f) f = pick(plan.rpw, plan.nseg, plan.pro, plan.epi, fs);
+  KernelFn f = pick(plan.rpw, plan.nseg, plan.pro, plan.epi);
   if (!f) {
-    set_error("gemv: no kernel instantiation (nseg=%d pro=%d epi=%d flag-sync=%d)", plan.nseg, plan.pro, plan.epi, (int)fs);
+    set_error("gemv: no kernel instantiation (nseg=%d pro=%d epi=%d)", plan.nseg, plan.pro, plan.epi);
     return B200_ERR_INVALID;
   }
-  B200_CUDA(launch_pdl(f, dim3(plan.grid), dim3(kThreads), (size_t)plan.smem, stream, pdl, plan.p, plan.tmap,
-                       plan.pf_tmap));
+  B200_CUDA(launch_pdl(f, dim3(plan.grid), dim3(kThreads), (size_t)plan.smem, stream, pdl, plan.p, plan.tmap));
   return B200_OK;
 }
 

@@ -33,17 +33,6 @@ struct GemvParams {
   int stages;                     // depth of the shared-memory ring
   unsigned long long* trace;      // debug (B200_TRACE=1): CTA 0 stores globaltimer at entry / after the PDL wait / at exit
   int* pos_inc;                   // engine: when set, CTA 0 advances the token position after its last row block
-  unsigned long long* epoch_inc;  // flag-sync engines: … and the count of completed tokens (with pos_inc)
-  FlagSync fs;                    // opt-in flag synchronisation (common.cuh); fs.signal_ctr == null ⇒ plain PDL kernel
-  // opt-in cross-kernel L2 prefetch (B200_L2PF_MB): once this kernel's producer has issued its last TMA load it asks
-  // L2 — with the NEXT GEMV's own tensor map, box by box, in that kernel's own streaming order — for the pipeline
-  // stages that lie just beyond what the next kernel's rings hold (stage indices [pf_begin, pf_begin + pf_count) of
-  // every CTA of the next kernel), so that HBM keeps streaming through this kernel's tail, the kernel boundary and the
-  // next prologue.  Hint only: no effect on results.  pf_count == 0 ⇒ nothing.
-  int pf_begin, pf_count;         // stage range per CTA of the next kernel
-  int pf_grid, pf_rowblocks;      // the next kernel's grid and row blocks
-  int pf_ksteps, pf_kb, pf_nseg;  // … its k steps per row block, 256-column boxes per stage, segments
-  int pf_box_r, pf_seg_rows;      // … its box height and the row offset of segment 1
   // ---- tensor-parallel exchange (peer-mapped windows over NVLink).  Low-latency protocol: every fp32 partial travels
   // as ONE 8-byte store {value bits, tag} with tag = token epoch + 1, so data and "flag" arrive atomically together —
   // no system fence, no remote atomic, no separate flag poll (the idea of NCCL's LL protocol).
@@ -58,7 +47,6 @@ struct GemvParams {
 
 struct GemvPlan {
   CUtensorMap tmap;
-  CUtensorMap pf_tmap;  // tensor map of the NEXT GEMV when cross-kernel prefetch is planned, else a copy of tmap
   GemvParams p;
   int rpw;   // rows per consumer warp: 1, 2 or 4
   int nseg;  // 1, or 2 for merged gate|up
@@ -66,7 +54,6 @@ struct GemvPlan {
   int epi;
   int grid;
   int smem;
-  bool smallk;  // opt-in (B200_GEMV_SMALLK=1): register-resident activation vector, batched reductions/epilogues
 };
 
 // Plan a GEMV over W[rows_total, k] (row-major bf16).  `n` = rows produced (per segment).
@@ -79,9 +66,6 @@ int gemv_make_plan(GemvPlan* plan, const void* W, int64_t rows_total, int64_t n,
                    int num_sms, int smem_budget = kGemvDefaultSmem);
 int gemv_smem_wanted(int64_t n, int64_t k, int nseg, int num_sms);
 int gemv_launch(const GemvPlan& plan, cudaStream_t stream, bool pdl);
-// Fill cur.p.pf_* / cur.pf_tmap so that `cur` prefetches into L2 what `next` will stream right after its rings are
-// full: at most budget_bytes chip-wide, in next's own stage order.
-void gemv_plan_prefetch(GemvPlan* cur, const GemvPlan& next, int64_t budget_bytes);
 int gemv_setup_attributes();  // cudaFuncSetAttribute(max dynamic smem) for every instantiation, once per process
 
 }  // namespace b200

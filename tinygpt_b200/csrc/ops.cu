@@ -221,7 +221,6 @@ __global__ void __launch_bounds__(256) argmax_kernel(int64_t* __restrict__ out, 
       // engine: the greedy token becomes the next step's input and is appended to the on-device log
       *pub.cur_tok = idx;
       if (pub.pos != nullptr) *pub.pos += 1;
-      if (pub.epoch_inc != nullptr) *pub.epoch_inc += 1ull;
       const unsigned long long c = *pub.gen_count;
       pub.gen_log[c % (unsigned long long)pub.gen_cap] = idx;
       *pub.gen_count = c + 1;

@@ -23,7 +23,6 @@ struct ArgmaxPublish {
   int gen_cap = 1;
   // tensor parallel (vocabulary-sharded lm_head): instead of publishing, push (max logit, GLOBAL index) into every
   // rank's candidate slot and bump its arrival counter; tp_finish_kernel (engine.cu) picks the winner.
-  unsigned long long* epoch_inc = nullptr;  // flag-sync engines: count of completed tokens, advanced with pos
   // async token pipeline: ring in pinned, device-mapped host memory (b200_engine_set_mailbox); null = none
   unsigned long long* mailbox = nullptr;
   unsigned long long mailbox_cap = 1;
@@ -78,7 +77,6 @@ struct AttnDecodeParams {
   unsigned int* tickets;         // [Hq], zero-initialised, self-resetting
   int heads_per_cta;             // 0 = choose from max_ctx (attn_heads_per_cta)
   unsigned long long* trace;     // debug timestamps (see GemvParams::trace)
-  FlagSync fs;                   // opt-in flag synchronisation (common.cuh); signal_ctr == null ⇒ plain PDL kernel
   int Hq, Hkv, nsplit, max_ctx;  // nsplit = attn_decode_nsplit(hd, max_ctx): fixed 256 (hd 64) / 128 (hd 128) keys per split
 };
 int attn_decode_nsplit(int hd, int max_ctx);

@@ -320,7 +320,6 @@ __global__ void __launch_bounds__(kDrawThreads) sample_draw_kernel(const __nv_bf
     if (pub.cur_tok != nullptr) {   // same publication as argmax_kernel (ops.cu)
       *pub.cur_tok = pick;
       if (pub.pos != nullptr) *pub.pos += 1;
-      if (pub.epoch_inc != nullptr) *pub.epoch_inc += 1ull;
       const unsigned long long c = *pub.gen_count;
       pub.gen_log[c % (unsigned long long)pub.gen_cap] = pick;
       *pub.gen_count = c + 1;

@@ -34,7 +34,14 @@ class DecodeEngine:
             raise B200Error("DecodeEngine: weights must be on a CUDA device (no CPU path)")
         self.device = dev
         self._w = weights  # keep alive
-        self._rope = (models.rope_table(spec) if rope_table is None else rope_table).to(dev).contiguous()
+        if rope_table is None:
+            # built on the device by the same fp32 powf/cosf/sinf kernels as the reference's op::ropeInit, so the table
+            # is the one RoPE::cache() holds in a TinyGPT process (models.rope_table is the host/numpy restatement the
+            # CPU oracle uses; libm and CUDA differ in the last bit of a few entries)
+            from . import ops
+            with torch.cuda.device(dev):
+                rope_table = ops.rope_init(spec.head_dim, spec.max_ctx, spec.rope_theta, spec.rope_scaling, device=dev)
+        self._rope = rope_table.to(dev).contiguous()
         self.local_vocab = spec.vocab
         desc, table = self._describe(spec, weights, rank=0, world=1, shard_attn=True)
         h = C.c_void_p()
@@ -89,6 +96,11 @@ class DecodeEngine:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     @property
+    def rope_table(self) -> torch.Tensor:
+        """fp32 [max_ctx, head_dim, 2] cos/sin table the engine rotates with."""
+        return self._rope
+
+    @property
     def position(self) -> int:
         return int(lib().b200_engine_position(self._h))
 
@@ -100,8 +112,7 @@ class DecodeEngine:
     def options(self) -> dict:
         """Code paths this engine was built with (b200_engine_options)."""
         o = int(lib().b200_engine_options(self._h))
-        return {"cuda_graph": bool(o & 1), "pdl": bool(o & 2), "flag_sync": bool(o & 4), "gemm_prefill": bool(o & 8),
-                "l2_prefetch_mb": (o >> 8) & 0xFF}
+        return {"cuda_graph": bool(o & 1), "pdl": bool(o & 2), "gemm_prefill": bool(o & 8)}
 
     def bytes_per_token(self, ctx: int) -> int:
         return int(lib().b200_engine_bytes_per_token(self._h, ctx))

@@ -80,7 +80,11 @@ class TPDecodeEngine(DecodeEngine):
             shard_attn = can_shard_attention(spec, world)
         self.spec, self.device, self.rank, self.world, self.shard_attn = spec, device, rank, world, shard_attn
         self._w = {k: v.to(device) for k, v in shard_weights(spec, weights, rank, world, shard_attn).items()}
-        self._rope = (models.rope_table(spec) if rope_table is None else rope_table).to(device).contiguous()
+        if rope_table is None:  # device-built like the reference's op::ropeInit (see DecodeEngine)
+            from . import ops
+            with torch.cuda.device(device):
+                rope_table = ops.rope_init(spec.head_dim, spec.max_ctx, spec.rope_theta, spec.rope_scaling, device=device)
+        self._rope = rope_table.to(device).contiguous()
         self.local_vocab = spec.vocab // world
         desc, table = self._describe(spec, self._w, rank, world, shard_attn)
         # exchange windows: create mine, export, gather everybody's handles, map the peers

@@ -35,7 +35,8 @@ REF_BIN = ROOT / "oracle" / "_ref" / "ref_cuda_decode"
 FAMILY = {"llama": "llama", "qwen2": "qwen2", "qwen3": "qwen3", "mistral": "mistral"}
 
 
-def run_reference(spec, ckpt_dir, prompt, n_new, forced=None, time_steps=0, timeout=1200, b200="off"):
+def run_reference(spec, ckpt_dir, prompt, n_new, forced=None, time_steps=0, timeout=1200, b200="off", batched=False,
+                  dump_rope=None):
     """→ (tokens [n_new] int64, logits [n_new, V] float32, timing dict or None) from the reference CUDA binary.
     b200 = "ops" / "engine": the same reference program with our kernels behind its op registry (boundary B) / our
     engine behind GPTModel::model() (boundary A), through integration/tinytorch_b200_adapter.h."""
@@ -55,6 +56,10 @@ def run_reference(spec, ckpt_dir, prompt, n_new, forced=None, time_steps=0, time
         cmd += ["--forced", str(d / "forced.bin")]
     if time_steps:
         cmd += ["--time-steps", str(time_steps)]
+    if batched:
+        cmd += ["--batched", "1"]
+    if dump_rope:
+        cmd += ["--dump-rope", str(dump_rope)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
     if r.returncode != 0:
         raise RuntimeError(f"ref_cuda_decode failed ({r.returncode}): {r.stderr[-800:]}")
@@ -129,7 +134,24 @@ def main():
             toks, logits, us = run_engine(spec, w, prompt, args.new)
             ref_toks_forced, ref_logits, _ = run_reference(spec, td, prompt, args.new, forced=toks.tolist())
             ref_toks_free, _, timing = run_reference(spec, td, prompt, args.new, time_steps=128 if big else 32)
-        row = {"model": name, "engine_vs_reference_cuda": compare("engine-ref", logits, ref_logits)}
+            # the reference against itself: the same positions through its batched path (one forward over prompt +
+            # forced tokens: cuBLAS GEMM m > 1, causal TinyFA) — the noise floor of its own CUDA arithmetic
+            _, ref_logits_batched, _ = run_reference(spec, td, prompt, args.new, forced=toks.tolist(), batched=True,
+                                                     dump_rope=Path(td) / "rope.bin")
+            raw = (Path(td) / "rope.bin").read_bytes()
+            shp = np.frombuffer(raw[:24], dtype=np.int64)
+            ref_rope = torch.from_numpy(np.frombuffer(raw[24:], dtype=np.float32).reshape(*shp).copy())
+        row = {"model": name, "engine_vs_reference_cuda": compare("engine-ref", logits, ref_logits),
+               "reference_cuda_decode_vs_its_own_batched_path": compare("ref-ref", ref_logits_batched, ref_logits)}
+        from tinygpt_b200 import ops as b200ops
+        rows = min(int(shp[0]), spec.max_ctx)
+        dev_tab = b200ops.rope_init(spec.head_dim, rows, spec.rope_theta, spec.rope_scaling).cpu()
+        host_tab = models.rope_table(spec)[:rows]
+        row["rope_table"] = {"reference_rows": int(shp[0]), "compared_rows": rows,
+                             "b200_rope_init_bit_identical": bool(torch.equal(dev_tab, ref_rope[:rows])),
+                             "b200_rope_init_max_abs": float((dev_tab - ref_rope[:rows]).abs().max()),
+                             "host_numpy_table_frac_identical": float((host_tab == ref_rope[:rows]).float().mean()),
+                             "host_numpy_table_max_abs": float((host_tab - ref_rope[:rows]).abs().max())}
         # greedy ids: the reference's argmax on ITS logits, forced on our tokens, step by step
         top2 = torch.topk(ref_logits, 2, dim=-1).values
         margin = (top2[:, 0] - top2[:, 1])
@@ -152,7 +174,7 @@ def main():
         if n_params <= args.oracle_max_params:
             wf = {k: v.float().cpu() for k, v in w.items()}
             _, logits_orc = orc.generate_greedy(to_oracle_cfg(spec), wf, torch.tensor(prompt), args.new,
-                                                models.rope_table(spec), "bf16", forced=toks)
+                                                ref_rope[:rows].contiguous(), "bf16", forced=toks)  # the reference's table
             row["oracle_vs_reference_cuda"] = compare("oracle-ref", logits_orc, ref_logits)
             row["engine_vs_oracle"] = compare("engine-oracle", logits, logits_orc)
             del wf
