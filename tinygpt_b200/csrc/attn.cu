@@ -307,6 +307,243 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnDec
   if (tid == 0) p.tickets[hg] = 0;
 }
 
+
+// ------------------------------------------------------------------------------------------ register-resident variant
+// Same work split and the same arithmetic as attn_decode_kernel, rearranged for latency (in-kernel stamps of the
+// shared-memory kernel: 2.0 µs per launch at ctx ≈ 80 of which q/k/v staging 0.54, scores 0.54, softmax 0.64, P·V
+// 0.3 — five CTA barriers around 69 KB of traffic):
+//   * thread = (key group, 16-byte piece): the K and V pieces of up to 8 cached rows per thread are loaded into
+//     REGISTERS before griddepcontrol.wait (the rows were written by earlier tokens), no shared-memory staging;
+//   * after the wait: q/k RMSNorm + RoPE by one warp per head as before, ONE barrier, then every thread runs an online
+//     softmax over its own ≤ 8 keys (scores never leave registers), the key groups of a warp merge by xor-shuffle, the
+//     8 warps through 5 KB of shared memory: two more barriers per query head, none for scores / softmax / P·V.
+// The new K/V row is written in place to the cache and handed to the owning thread through shared memory.
+template <int HD>
+__global__ void __launch_bounds__(kAttnThreads) attn_decode_reg_kernel(const AttnDecodeParams p, const int G) {
+  constexpr int LPK = HD / 8;             // lanes per key row
+  constexpr int NG = kAttnThreads / LPK;  // key rows per pass
+  constexpr int KPT = 8;                  // key rows per thread
+  constexpr int CHUNK = NG * KPT;         // = SplitKeys<HD>: 256 (hd 64) / 128 (hd 128)
+  static_assert(CHUNK == SplitKeys<HD>::value, "split size is shared with the host-side nsplit");
+  constexpr int EPL = HD / 32;
+  constexpr float kScale = InvSqrtHd<HD>::value * kLog2e;
+  __shared__ float q_s[8 * HD];
+  __shared__ __align__(16) __nv_bfloat16 knew[HD];
+  __shared__ __align__(16) __nv_bfloat16 vnew[HD];
+  __shared__ float ared[kAttnWarps * 16 * 10];
+  __shared__ int is_last;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int hg = blockIdx.y, split = blockIdx.x;
+  const int h0 = hg * G;
+  const int group = p.Hq / p.Hkv;
+  const int kvh = h0 / group;
+  const bool kv_leader = (h0 % group) == 0;
+  if (p.trace != nullptr && hg == 0 && split == 0 && tid == 0) p.trace[0] = global_timer_ns();
+  pdl_trigger();
+  const bool append = (p.pos != nullptr);
+  const int pos = append ? *p.pos : p.fixed_len - 1;   // stable since before the producer kernel started (engine.cu)
+  const int L = pos + 1;
+  const int nact = (L + CHUNK - 1) / CHUNK;
+  if (split >= nact) {
+    pdl_wait();
+    return;
+  }
+  const int start = split * CHUNK;
+  const int end = min(L, start + CHUNK);
+  const int n_old_end = append ? min(end, pos) : end;    // rows [start, n_old_end) are already in the cache
+  const bool owns_new = append && pos >= start && pos < end;
+  const int grp = tid / LPK, part = tid % LPK;
+  const int imax = (end - start + NG - 1) / NG;   // key slots per thread that this split can fill (CTA-uniform)
+
+  uint4 kreg[KPT], vreg[KPT];
+#pragma unroll
+  for (int i = 0; i < KPT; ++i) {
+    const int row = start + grp + NG * i;
+    kreg[i] = make_uint4(0, 0, 0, 0);
+    vreg[i] = make_uint4(0, 0, 0, 0);
+    if (i < imax && row < n_old_end) {
+      const size_t g = ((size_t)row * p.Hkv + kvh) * HD + part * 8;
+      kreg[i] = *reinterpret_cast<const uint4*>(p.kcache + g);
+      vreg[i] = *reinterpret_cast<const uint4*>(p.vcache + g);
+    }
+  }
+  float rc[EPL / 2], rs[EPL / 2];
+  if (p.rope != nullptr) {
+    const float* row = p.rope + (size_t)pos * HD * 2;
+#pragma unroll
+    for (int j = 0; j < EPL / 2; ++j) {
+      rc[j] = row[(lane + 32 * j) * 2];
+      rs[j] = row[(lane + 32 * j) * 2 + 1];
+    }
+  }
+  pdl_wait();   // qkv of this token is complete and visible from here on
+  if (p.trace != nullptr && hg == 0 && split == 0 && tid == 0) p.trace[1] = global_timer_ns();
+  const int qdim = p.Hq * HD, kvdim = p.Hkv * HD;
+  for (int h = warp; h < G + 1; h += kAttnWarps) {
+    const bool is_k = (h == G);
+    if (is_k && !owns_new) break;
+    const __nv_bfloat16* src = is_k ? p.qkv + qdim + kvh * HD : p.qkv + (h0 + h) * HD;
+    const __nv_bfloat16* nw = is_k ? p.k_norm : p.q_norm;
+    float x[EPL];
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) x[j] = bf16_to_f(src[lane + 32 * j]);
+    if (nw != nullptr) {
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) ss += x[j] * x[j];
+      ss = warp_sum(ss);
+      const float inv = rsqrtf(ss / (float)HD + p.eps);
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) x[j] = round_bf16(x[j] * inv * bf16_to_f(nw[lane + 32 * j]));
+    }
+    if (p.rope != nullptr) {
+#pragma unroll
+      for (int j = 0; j < EPL / 2; ++j) {
+        const float x1 = x[j], x2 = x[j + EPL / 2];
+        x[j] = round_bf16(x1 * rc[j] - x2 * rs[j]);
+        x[j + EPL / 2] = round_bf16(x2 * rc[j] + x1 * rs[j]);
+      }
+    }
+    if (is_k) {
+      __nv_bfloat16* kg = p.kcache + ((size_t)pos * p.Hkv + kvh) * HD;
+      __nv_bfloat16* vg = p.vcache + ((size_t)pos * p.Hkv + kvh) * HD;
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) {
+        const __nv_bfloat16 kk = f_to_bf16(x[j]);
+        const __nv_bfloat16 vv = p.qkv[qdim + kvdim + kvh * HD + lane + 32 * j];
+        knew[lane + 32 * j] = kk;
+        vnew[lane + 32 * j] = vv;
+        if (kv_leader) {
+          kg[lane + 32 * j] = kk;
+          vg[lane + 32 * j] = vv;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) q_s[h * HD + lane + 32 * j] = x[j];
+    }
+  }
+  __syncthreads();
+  if (p.trace != nullptr && hg == 0 && split == 0 && tid == 0) p.trace[3] = global_timer_ns();
+  if (owns_new) {
+#pragma unroll
+    for (int i = 0; i < KPT; ++i) {
+      if (start + grp + NG * i == pos) {
+        kreg[i] = reinterpret_cast<const uint4*>(knew)[part];
+        vreg[i] = reinterpret_cast<const uint4*>(vnew)[part];
+      }
+    }
+  }
+  for (int g = 0; g < G; ++g) {
+    float qf[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) qf[e] = q_s[g * HD + part * 8 + e];
+    float sc[KPT];
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < KPT; ++i) {
+      sc[i] = -INFINITY;
+      if (i < imax) {   // uniform: unused slots cost one branch
+        float d = dot8(kreg[i], qf, 0.f);
+#pragma unroll
+        for (int o = LPK / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        if ((start + grp + NG * i) < end) sc[i] = d;
+        m = fmaxf(m, sc[i]);
+      }
+    }
+    float l = 0.f, acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    const float m_scaled = m * kScale;
+#pragma unroll
+    for (int i = 0; i < KPT; ++i) {
+      if (i < imax) {
+        const float pr = (sc[i] == -INFINITY) ? 0.f : exp2f(sc[i] * kScale - m_scaled);
+        l += pr;
+        float vf[8];
+        unpack8(vreg[i], vf);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(pr, vf[e], acc[e]);
+      }
+    }
+#pragma unroll
+    for (int o = LPK; o < 32; o <<= 1) {   // key groups that live in the same warp
+      const float mo = __shfl_xor_sync(0xffffffffu, m, o);
+      const float lo = __shfl_xor_sync(0xffffffffu, l, o);
+      const float mn = fmaxf(m, mo);
+      const float a = (m == -INFINITY) ? 0.f : exp2f((m - mn) * kScale);
+      const float b = (mo == -INFINITY) ? 0.f : exp2f((mo - mn) * kScale);
+      l = l * a + lo * b;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float ao = __shfl_xor_sync(0xffffffffu, acc[e], o);
+        acc[e] = acc[e] * a + ao * b;
+      }
+      m = mn;
+    }
+    if (lane < LPK) {
+      float* r = ared + (warp * 16 + lane) * 10;
+      r[0] = m;
+      r[1] = l;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) r[2 + e] = acc[e];
+    }
+    __syncthreads();
+    if (tid < HD) {
+      const int d = tid, pt = d >> 3, e = d & 7;
+      float M = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < kAttnWarps; ++w) M = fmaxf(M, ared[(w * 16 + pt) * 10]);
+      float num = 0.f, den = 0.f;
+#pragma unroll
+      for (int w = 0; w < kAttnWarps; ++w) {
+        const float* r = ared + (w * 16 + pt) * 10;
+        const float wgt = (r[0] == -INFINITY) ? 0.f : exp2f((r[0] - M) * kScale);
+        num = fmaf(wgt, r[2 + e], num);
+        den = fmaf(wgt, r[1], den);
+      }
+      if (nact == 1) {
+        p.out[(h0 + g) * HD + d] = f_to_bf16(num * (den > 0.f ? 1.f / den : 0.f));
+      } else {
+        float* wsr = p.ws + ((size_t)(h0 + g) * p.nsplit + split) * (HD + 2);
+        wsr[d] = num;
+        if (d == 0) {
+          wsr[HD] = M;
+          wsr[HD + 1] = den;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (p.trace != nullptr && hg == 0 && split == 0 && tid == 0) p.trace[2] = global_timer_ns();
+  if (nact == 1) return;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int t = atomicAdd(&p.tickets[hg], 1u);
+    is_last = (t == (unsigned int)nact - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int idx = tid; idx < G * HD; idx += kAttnThreads) {
+    const int g = idx / HD, d = idx % HD;
+    const float* base = p.ws + (size_t)(h0 + g) * p.nsplit * (HD + 2);
+    float M = -INFINITY;
+    for (int s = 0; s < nact; ++s) M = fmaxf(M, __ldcg(base + (size_t)s * (HD + 2) + HD));
+    float num = 0.f, den = 0.f;
+    for (int s = 0; s < nact; ++s) {
+      const float* r = base + (size_t)s * (HD + 2);
+      const float w = exp2f((__ldcg(r + HD) - M) * kScale);
+      num = fmaf(w, __ldcg(r + d), num);
+      den = fmaf(w, __ldcg(r + HD + 1), den);
+    }
+    p.out[(h0 + g) * HD + d] = f_to_bf16(num * (den > 0.f ? 1.f / den : 0.f));
+  }
+  if (tid == 0) p.tickets[hg] = 0;
+}
+
 using AttnFn = void (*)(const AttnDecodeParams);
 
 template <int HD>
@@ -436,16 +673,23 @@ int launch_attn_decode(const AttnDecodeParams& p, int hd, cudaStream_t st, bool 
   B200_CHECK_ARG(p.Hkv > 0 && p.Hq % p.Hkv == 0, "attention: Hq=%d must be a multiple of Hkv=%d", p.Hq, p.Hkv);
   const int G = p.heads_per_cta > 0 ? p.heads_per_cta : attn_heads_per_cta(p.Hq, p.Hkv, p.max_ctx);
   B200_CHECK_ARG((p.Hq / p.Hkv) % G == 0, "attention: heads per CTA %d must divide the GQA group %d", G, p.Hq / p.Hkv);
+  B200_CHECK_ARG(p.max_ctx >= 1 && p.nsplit == attn_decode_nsplit(hd, p.max_ctx),
+                 "attention: nsplit %d does not match max_ctx %d (need %d)", p.nsplit, p.max_ctx,
+                 attn_decode_nsplit(hd, p.max_ctx));
+  B200_CHECK_ARG(p.nsplit <= 65535, "attention: context too long");
+  if (env_choice("B200_ATTN", 'r', true) && G <= 8) {   // "reg" (default) | "smem": the register-resident kernel
+    if (hd == 64)
+      B200_CUDA(launch_pdl(attn_decode_reg_kernel<64>, dim3(p.nsplit, p.Hq / G), dim3(kAttnThreads), 0, st, pdl, p, G));
+    else
+      B200_CUDA(launch_pdl(attn_decode_reg_kernel<128>, dim3(p.nsplit, p.Hq / G), dim3(kAttnThreads), 0, st, pdl, p, G));
+    return B200_OK;
+  }
   AttnFn f = (hd == 64) ? pick_attn<64>(G) : pick_attn<128>(G);
   if (!f) {
     set_error("attention: %d query heads per CTA not built (1,2,3,4,7,8 are)", G);
     return B200_ERR_UNSUPPORTED;
   }
   const int chunk = (hd == 64) ? SplitKeys<64>::value : SplitKeys<128>::value;
-  B200_CHECK_ARG(p.max_ctx >= 1 && p.nsplit == attn_decode_nsplit(hd, p.max_ctx),
-                 "attention: nsplit %d does not match max_ctx %d (need %d)", p.nsplit, p.max_ctx,
-                 attn_decode_nsplit(hd, p.max_ctx));
-  B200_CHECK_ARG(p.nsplit <= 65535, "attention: context too long");
   const size_t smem = (size_t)2 * chunk * hd * 2 + (size_t)(G * hd + kAttnWarps * G * hd + G * chunk + 2 * G) * 4;
   B200_CUDA(launch_pdl(f, dim3(p.nsplit, p.Hq / G), dim3(kAttnThreads), smem, st, pdl, p));
   return B200_OK;

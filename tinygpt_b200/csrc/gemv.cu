@@ -137,7 +137,12 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
   auto ldx = [](const uint4* q) -> uint4 { return *q; };
   unsigned int tp_tag = 0;
   if constexpr (EPI == EPI_TP_PUSH) tp_tag = (unsigned int)(*p.tp_epoch + 1ull);
-  if (p.trace != nullptr && blockIdx.x == 0 && ctid == 0) p.trace[1] = global_timer_ns();
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0 && ctid == 0;
+  long long c0 = 0;
+  if (tracing) {
+    p.trace[1] = global_timer_ns();
+    c0 = clock64();   // SM cycles from here: slots 4-7 = first stage landed, first row block summed / stored, last stored
+  }
 
   if constexpr (PRO == PRO_PLAIN) {
     const uint4* xg = reinterpret_cast<const uint4*>(p.x);
@@ -289,6 +294,7 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
       for (int kb = 0; kb < KB; ++kb)
         xq[kb] = *reinterpret_cast<const uint4*>(xs + (ks * KB + kb) * kBoxK + lane * 8);
       mbar_wait(&full[s], ph);
+      if (tracing && i == 0 && ks == 0) p.trace[4] = (unsigned long long)(clock64() - c0);
       const uint8_t* st = my_rows + (size_t)s * kStageBytes;
       uint4 wv[KB][NSEG][RPW];
 #pragma unroll
@@ -315,6 +321,7 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
       }
     }
 
+    if (tracing && i == 0) p.trace[5] = (unsigned long long)(clock64() - c0);
 #pragma unroll
     for (int seg = 0; seg < NSEG; ++seg)
 #pragma unroll
@@ -346,6 +353,7 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
         for (int q = 0; q < p.tp_world; ++q) st_volatile_u2(p.tp_push[q] + row, pk);
       }
     }
+    if (tracing) p.trace[i == 0 ? 6 : 7] = (unsigned long long)(clock64() - c0);
   }
 
   if (p.pos_inc != nullptr && blockIdx.x == 0 && ctid == 0) *p.pos_inc += 1;

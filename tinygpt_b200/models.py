@@ -87,9 +87,12 @@ TINY_QWEN3 = ModelSpec("tiny-qwen3", "qwen3", 192, 2, 4, 2, 128, 320, 384, 1e6, 
                        max_ctx=256)
 TINY_MISTRAL = ModelSpec("tiny-mistral", "mistral", 1024, 2, 8, 2, 128, 448, 512, 1e6, 1e-5, tie=False, max_ctx=256)
 
+# 8 KV heads: attention heads shard over 2, 4 and 8 tensor-parallel ranks (the other tiny shapes have 2 KV heads)
+TINY_TP8 = ModelSpec("tiny-tp8", "mistral", 1024, 2, 8, 8, 128, 512, 1024, 1e6, 1e-5, tie=False, max_ctx=256)
+
 SPECS: Dict[str, ModelSpec] = {s.name: s for s in
                                (QWEN25_05B, LLAMA32_3B, QWEN3_17B, MISTRAL_7B, TINY_QWEN2, TINY_LLAMA, TINY_QWEN3,
-                                TINY_MISTRAL)}
+                                TINY_MISTRAL, TINY_TP8)}
 
 
 def synth_weights(spec: ModelSpec, seed: int = 0, device: str = "cpu", std: float = 0.02,
