@@ -252,6 +252,19 @@ class Dist:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # rank 0 does some work alone (one-GPU baselines, CPU baseline, printing): the other ranks must SLEEP meanwhile — a
+    # NCCL barrier would keep their host threads and GPUs spinning next to the measurement
+    def set_key(self, key: str):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.distributed_c10d._get_default_store().set(key, "1")
+
+    def wait_key(self, key: str, timeout_s: int = 900):
+        if self.world > 1:
+            import datetime
+            import torch.distributed as dist
+            dist.distributed_c10d._get_default_store().wait([key], datetime.timedelta(seconds=timeout_s))
+
     def max(self, x: float) -> float:
         import torch
         if self.world == 1:
@@ -367,8 +380,10 @@ def measure_extra_model(name, world, rank, dev, d: Dist, steps, tp_mode):
                                        "frac": bytes_tok / one_gpu_ms / 1e6 / peak, "bytes_per_token": bytes_tok}}
         eng1.close()
         del eng1
+        d.set_key(f"one_gpu_{name}")
     if world > 1 and tp_mode:
         from tinygpt_b200 import tp
+        d.wait_key(f"one_gpu_{name}")
         d.barrier()
         eng = tp.TPDecodeEngine(spec, w_full, rank, world, dev)
         del w_full
@@ -504,9 +519,10 @@ def run_ours(args):
         eng = eng_keep
 
     if rank != 0:
+        d.wait_key("rank0_done")
         eng.close()
-        if world > 1:
-            dist.destroy_process_group()
+        dist.barrier()
+        dist.destroy_process_group()
         return
 
     # ---- roofline (rank 0)
@@ -598,8 +614,10 @@ def run_ours(args):
     if ref_cuda is not None:
         line["reference_cuda_baseline"] = ref_cuda
     print(json.dumps(line), flush=True)
+    d.set_key("rank0_done")
     eng.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

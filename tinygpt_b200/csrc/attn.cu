@@ -37,11 +37,6 @@ struct InvSqrtHd<128> {
   static constexpr float value = 0.08838834764831845f;
 };
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // keys per split: fixed by the shared-memory staging buffers (K and V of one split = 64 KB for both head dims)
 template <int HD>
@@ -49,269 +44,12 @@ struct SplitKeys {
   static constexpr int value = (HD == 64) ? 256 : 128;
 };
 
-template <int HD, int G>
-__global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnDecodeParams p) {
-  constexpr int LPK = HD / 8;           // lanes per key row (16-byte pieces)
-  constexpr int KPW = 32 / LPK;         // keys per warp per iteration
-  constexpr int NSLOT = kAttnThreads / LPK;
-  constexpr int EPL = HD / 32;          // elements per lane when a warp owns one head vector
-  constexpr int CHUNK = SplitKeys<HD>::value;
-  constexpr float kScale = InvSqrtHd<HD>::value * kLog2e;
-
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  __nv_bfloat16* kbuf = reinterpret_cast<__nv_bfloat16*>(smem_raw);      // [CHUNK][HD]
-  __nv_bfloat16* vbuf = kbuf + CHUNK * HD;                                // [CHUNK][HD]
-  float* q_s = reinterpret_cast<float*>(vbuf + CHUNK * HD);               // [G][HD]
-  float* pv_red = q_s + G * HD;                                           // [8][G][HD]
-  float* sc = pv_red + kAttnWarps * G * HD;                               // [G][CHUNK]
-  float* ml = sc + G * CHUNK;                                             // [G][2]
-  __shared__ bool is_last;
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // CTA = (KV split, group of G query heads that share one KV head).  G == Hq/Hkv: K/V read once per KV head (long
-  // contexts); G == 1: one CTA per query head, K/V re-read from L2 but Hq CTAs share the latency-bound work (short
-  // contexts).  `hg` indexes the head group, `kvh` its KV head; only the first group of a KV head appends the new row.
-  const int hg = blockIdx.y, split = blockIdx.x;
-  const int h0 = hg * G;
-  const int group = p.Hq / p.Hkv;
-  const int kvh = h0 / group;
-  const bool kv_leader = (h0 % group) == 0;
-
-  if (p.trace != nullptr && hg == 0 && split == 0 && tid == 0) p.trace[0] = global_timer_ns();
-  pdl_trigger();
-  // *p.pos was written by the PREVIOUS token's last kernel (or by reset/seek), i.e. before this graph launch began, so
-  // it may be read ahead of griddepcontrol.wait — and with it every cached K/V row below pos.
-  const bool append = (p.pos != nullptr);
-  const int pos = append ? *p.pos : p.fixed_len - 1;
-  const int L = pos + 1;
-  const int nact = (L + CHUNK - 1) / CHUNK;
-  if (split >= nact) {
-    pdl_wait();
-    return;
-  }
-  const int start = split * CHUNK;
-  const int end = min(L, start + CHUNK);
-  const int nk = end - start;
-  const int n_old = append ? min(end, pos) - start : nk;  // rows already in the cache
-
-  // ---- stage the cached K/V rows of this split in shared memory (cp.async), overlapping the producer kernel
-  {
-    const int pieces = n_old * LPK;
-    for (int i = tid; i < pieces; i += kAttnThreads) {
-      const int r = i / LPK, c = i % LPK;
-      const size_t g = ((size_t)(start + r) * p.Hkv + kvh) * HD + c * 8;
-      cp_async16(kbuf + r * HD + c * 8, p.kcache + g);
-      cp_async16(vbuf + r * HD + c * 8, p.vcache + g);
-    }
-    cp_async_commit();
-  }
-  // RoPE row of this position (constant table)
-  float rc[EPL / 2], rs[EPL / 2];
-  if (p.rope != nullptr) {
-    const float* row = p.rope + (size_t)pos * HD * 2;
-#pragma unroll
-    for (int j = 0; j < EPL / 2; ++j) {
-      rc[j] = row[(lane + 32 * j) * 2];
-      rs[j] = row[(lane + 32 * j) * 2 + 1];
-    }
-  }
-
-  // qkv of this token is complete and visible from here on
-  pdl_wait();
-  auto ldq = [](const __nv_bfloat16* q) -> __nv_bfloat16 { return *q; };
-  if (p.trace != nullptr && hg == 0 && split == 0 && tid == 0) p.trace[1] = global_timer_ns();
-
-  const int qdim = p.Hq * HD, kvdim = p.Hkv * HD;
-  const bool owns_new = append && (pos >= start) && (pos < end);
-
-  // ---- q heads (and the new k/v): optional per-head RMSNorm, then RoPE, with the reference's roundings
-  for (int h = warp; h < G + 1; h += kAttnWarps) {
-    const bool is_k = (h == G);
-    if (is_k && !owns_new) break;
-    const __nv_bfloat16* src = is_k ? p.qkv + qdim + kvh * HD : p.qkv + (h0 + h) * HD;
-    const __nv_bfloat16* nw = is_k ? p.k_norm : p.q_norm;
-    float x[EPL];
-#pragma unroll
-    for (int j = 0; j < EPL; ++j) x[j] = bf16_to_f(ldq(src + lane + 32 * j));
-    if (nw != nullptr) {
-      float ss = 0.f;
-#pragma unroll
-      for (int j = 0; j < EPL; ++j) ss += x[j] * x[j];
-      ss = warp_sum(ss);
-      const float inv = rsqrtf(ss / (float)HD + p.eps);
-#pragma unroll
-      for (int j = 0; j < EPL; ++j) x[j] = round_bf16(x[j] * inv * bf16_to_f(nw[lane + 32 * j]));
-    }
-    if (p.rope != nullptr) {
-#pragma unroll
-      for (int j = 0; j < EPL / 2; ++j) {
-        const float x1 = x[j], x2 = x[j + EPL / 2];
-        x[j] = round_bf16(x1 * rc[j] - x2 * rs[j]);
-        x[j + EPL / 2] = round_bf16(x2 * rc[j] + x1 * rs[j]);
-      }
-    }
-    if (is_k) {
-      // the new row goes to its slot of the staged split and, in place, to the cache in HBM
-      __nv_bfloat16* krow = kbuf + (pos - start) * HD;
-      __nv_bfloat16* vrow = vbuf + (pos - start) * HD;
-      __nv_bfloat16* kg = p.kcache + ((size_t)pos * p.Hkv + kvh) * HD;
-      __nv_bfloat16* vg = p.vcache + ((size_t)pos * p.Hkv + kvh) * HD;
-#pragma unroll
-      for (int j = 0; j < EPL; ++j) {
-        const __nv_bfloat16 kk = f_to_bf16(x[j]);
-        const __nv_bfloat16 vv = ldq(p.qkv + qdim + kvdim + kvh * HD + lane + 32 * j);
-        krow[lane + 32 * j] = kk;
-        vrow[lane + 32 * j] = vv;
-        if (kv_leader) {
-          kg[lane + 32 * j] = kk;
-          vg[lane + 32 * j] = vv;
-        }
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < EPL; ++j) q_s[h * HD + lane + 32 * j] = x[j];
-    }
-  }
-  cp_async_wait_all();
-  __syncthreads();
-  if (p.trace != nullptr && hg == 0 && split == 0 && tid == 0) p.trace[3] = global_timer_ns();  // q/k/v staged
-
-  // ---- scores: LPK lanes cooperate on one key row, all G query heads at once
-  {
-    const int sub = lane / LPK, part = lane % LPK;
-    float qf[G][8];
-#pragma unroll
-    for (int g = 0; g < G; ++g)
-#pragma unroll
-      for (int e = 0; e < 8; ++e) qf[g][e] = q_s[g * HD + part * 8 + e];
-    for (int j0 = warp * KPW; j0 < nk; j0 += kAttnWarps * KPW) {
-      const int j = j0 + sub;
-      const bool valid = j < nk;
-      uint4 kv = make_uint4(0, 0, 0, 0);
-      if (valid) kv = *reinterpret_cast<const uint4*>(kbuf + j * HD + part * 8);
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        float d = dot8(kv, qf[g], 0.f);
-#pragma unroll
-        for (int o = LPK / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-        if (valid && part == 0) sc[g * CHUNK + j] = d;
-      }
-    }
-  }
-  __syncthreads();
-  if (p.trace != nullptr && hg == 0 && split == 0 && tid == 0) p.trace[4] = global_timer_ns();  // scores done
-
-  // ---- softmax inside the split (base-2 exponent like the reference): warp g owns head g
-  for (int g = warp; g < G; g += kAttnWarps) {
-    float* s = sc + g * CHUNK;
-    float m = -INFINITY;
-    for (int j = lane; j < nk; j += 32) m = fmaxf(m, s[j]);
-    m = warp_max(m);
-    const float m_scaled = m * kScale;
-    float l = 0.f;
-    for (int j = lane; j < nk; j += 32) {
-      const float e = exp2f(s[j] * kScale - m_scaled);
-      s[j] = e;
-      l += e;
-    }
-    l = warp_sum(l);
-    if (lane == 0) {
-      ml[g * 2] = m;
-      ml[g * 2 + 1] = l;
-    }
-  }
-  __syncthreads();
-  if (p.trace != nullptr && hg == 0 && split == 0 && tid == 0) p.trace[5] = global_timer_ns();  // softmax done
-
-  // ---- P·V: thread = (key slot, 16-byte piece of the V row); G×8 fp32 accumulators
-  {
-    const int slot = tid / LPK, part = tid % LPK;
-    float acc[G][8];
-#pragma unroll
-    for (int g = 0; g < G; ++g)
-#pragma unroll
-      for (int e = 0; e < 8; ++e) acc[g][e] = 0.f;
-    for (int j = slot; j < nk; j += NSLOT) {
-      const uint4 vv = *reinterpret_cast<const uint4*>(vbuf + j * HD + part * 8);
-      float vf[8];
-      unpack8(vv, vf);
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const float pj = sc[g * CHUNK + j];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[g][e] = fmaf(pj, vf[e], acc[g][e]);
-      }
-    }
-    // reduce over the key slots that live in the same warp, then across warps through shared memory
-#pragma unroll
-    for (int g = 0; g < G; ++g)
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        float v = acc[g][e];
-#pragma unroll
-        for (int o = LPK; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        acc[g][e] = v;
-      }
-    if (lane < LPK) {
-#pragma unroll
-      for (int g = 0; g < G; ++g)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) pv_red[(warp * G + g) * HD + lane * 8 + e] = acc[g][e];
-    }
-  }
-  __syncthreads();
-
-  if (p.trace != nullptr && hg == 0 && split == 0 && tid == 0) p.trace[2] = global_timer_ns();
-  float* ws_base = p.ws + ((size_t)hg * p.nsplit) * G * (HD + 2);
-  for (int idx = tid; idx < G * HD; idx += kAttnThreads) {
-    float o = 0.f;
-#pragma unroll
-    for (int w = 0; w < kAttnWarps; ++w) o += pv_red[w * G * HD + idx];
-    const int g = idx / HD, d = idx % HD;
-    if (nact == 1) {
-      const float l = ml[g * 2 + 1];
-      p.out[(h0 + g) * HD + d] = f_to_bf16(o * (l > 0.f ? 1.f / l : 0.f));
-    } else {
-      ws_base[((size_t)split * G + g) * (HD + 2) + d] = o;
-    }
-  }
-  if (nact == 1) return;
-  if (tid < G) {
-    ws_base[((size_t)split * G + tid) * (HD + 2) + HD] = ml[tid * 2];
-    ws_base[((size_t)split * G + tid) * (HD + 2) + HD + 1] = ml[tid * 2 + 1];
-  }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    const unsigned int t = atomicAdd(&p.tickets[hg], 1u);
-    is_last = (t == (unsigned int)nact - 1);
-  }
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-
-  // ---- merge the split partials (last CTA of this KV head)
-  for (int idx = tid; idx < G * HD; idx += kAttnThreads) {
-    const int g = idx / HD, d = idx % HD;
-    float M = -INFINITY;
-    for (int s = 0; s < nact; ++s) M = fmaxf(M, __ldcg(&ws_base[((size_t)s * G + g) * (HD + 2) + HD]));
-    float num = 0.f, den = 0.f;
-    for (int s = 0; s < nact; ++s) {
-      const float* r = &ws_base[((size_t)s * G + g) * (HD + 2)];
-      const float w = exp2f((__ldcg(&r[HD]) - M) * kScale);
-      num = fmaf(w, __ldcg(&r[d]), num);
-      den = fmaf(w, __ldcg(&r[HD + 1]), den);
-    }
-    p.out[(h0 + g) * HD + d] = f_to_bf16(num * (den > 0.f ? 1.f / den : 0.f));
-  }
-  if (tid == 0) p.tickets[hg] = 0;
-}
-
-
-// ------------------------------------------------------------------------------------------ register-resident variant
-// Same work split and the same arithmetic as attn_decode_kernel, rearranged for latency (in-kernel stamps of the
-// shared-memory kernel: 2.0 µs per launch at ctx ≈ 80 of which q/k/v staging 0.54, scores 0.54, softmax 0.64, P·V
-// 0.3 — five CTA barriers around 69 KB of traffic):
+// ------------------------------------------------------------------------------------------------- decode kernel
+// CTA = (KV split, group of G query heads that share one KV head).  Round 1 staged K/V of the split in shared memory
+// (cp.async) and ran scores / softmax / P·V as three barrier-separated phases: 2.0 µs per launch at ctx ≈ 80 for 69 KB
+// of traffic (in-kernel stamps: q/k/v staging 0.54, scores 0.54, softmax 0.64, P·V 0.3).  This kernel keeps everything
+// a thread needs in registers (measured against the staged kernel on B200: 409 vs 415 µs per Qwen2.5-0.5B token,
+// 1 425 vs 1 445 µs for Llama-3.2-3B, 1 106 vs 1 131 µs at ctx 2 048 for Qwen3-1.7B):
 //   * thread = (key group, 16-byte piece): the K and V pieces of up to 8 cached rows per thread are loaded into
 //     REGISTERS before griddepcontrol.wait (the rows were written by earlier tokens), no shared-memory staging;
 //   * after the wait: q/k RMSNorm + RoPE by one warp per head as before, ONE barrier, then every thread runs an online
@@ -544,21 +282,6 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_reg_kernel(const Att
   if (tid == 0) p.tickets[hg] = 0;
 }
 
-using AttnFn = void (*)(const AttnDecodeParams);
-
-template <int HD>
-AttnFn pick_attn(int G) {
-  switch (G) {
-    case 1: return attn_decode_kernel<HD, 1>;
-    case 2: return attn_decode_kernel<HD, 2>;
-    case 3: return attn_decode_kernel<HD, 3>;
-    case 4: return attn_decode_kernel<HD, 4>;
-    case 7: return attn_decode_kernel<HD, 7>;
-    case 8: return attn_decode_kernel<HD, 8>;
-  }
-  return nullptr;
-}
-
 // ------------------------------------------------------------------------------------------ general attention
 // One CTA per (q row, head, batch); keys in chunks of 128 with online softmax.  Correctness path (prefill-shaped
 // calls through b200_attn_bf16); the tensor-core prefill kernel is separate work.
@@ -629,39 +352,17 @@ int64_t attn_decode_ws_floats(int Hq, int Hkv, int hd, int nsplit) {
 }
 
 // Query heads per CTA: the whole GQA group once the context is long enough for K/V re-reads to matter, else one.
-// Only G in {1,2,3,4,7,8} is instantiated; any other group size (the reference accepts every Hq % Hkv == 0) falls back to
-// the largest instantiated divisor of the group (6 → 3, 5 → 1, 16 → 8, 12 → 4).
+// The kernel takes any G ≤ 8 that divides the GQA group (the reference accepts every Hq % Hkv == 0): the largest such
+// divisor (6 → 6, 5 → 5, 16 → 8, 12 → 6).
 int attn_heads_per_cta(int Hq, int Hkv, int max_ctx) {
   if (max_ctx <= 1024) return 1;
   const int group = Hq / Hkv;
-  const int built[6] = {8, 7, 4, 3, 2, 1};
-  for (int g : built)
+  for (int g = 8; g > 1; --g)
     if (group % g == 0) return g;
   return 1;
 }
 
-int attn_setup_attributes() {
-  static std::once_flag once;
-  static int rc = B200_OK;
-  std::call_once(once, [] {
-    const int gs[6] = {1, 2, 3, 4, 7, 8};
-    for (int g : gs) {
-      AttnFn fns[2] = {pick_attn<64>(g), pick_attn<128>(g)};
-      for (AttnFn f : fns) {
-        cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-        if (e == cudaSuccess)
-          e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) {
-          set_error("cudaFuncSetAttribute(attn smem) failed: %s", cudaGetErrorString(e));
-          rc = B200_ERR_CUDA;
-          (void)cudaGetLastError();
-          return;
-        }
-      }
-    }
-  });
-  return rc;
-}
+int attn_setup_attributes() { return B200_OK; }   // the decode kernel uses static shared memory only
 
 int attn_decode_nsplit(int hd, int max_ctx) {
   const int chunk = (hd == 64) ? SplitKeys<64>::value : SplitKeys<128>::value;
@@ -677,21 +378,11 @@ int launch_attn_decode(const AttnDecodeParams& p, int hd, cudaStream_t st, bool 
                  "attention: nsplit %d does not match max_ctx %d (need %d)", p.nsplit, p.max_ctx,
                  attn_decode_nsplit(hd, p.max_ctx));
   B200_CHECK_ARG(p.nsplit <= 65535, "attention: context too long");
-  if (env_choice("B200_ATTN", 'r', true) && G <= 8) {   // "reg" (default) | "smem": the register-resident kernel
-    if (hd == 64)
-      B200_CUDA(launch_pdl(attn_decode_reg_kernel<64>, dim3(p.nsplit, p.Hq / G), dim3(kAttnThreads), 0, st, pdl, p, G));
-    else
-      B200_CUDA(launch_pdl(attn_decode_reg_kernel<128>, dim3(p.nsplit, p.Hq / G), dim3(kAttnThreads), 0, st, pdl, p, G));
-    return B200_OK;
-  }
-  AttnFn f = (hd == 64) ? pick_attn<64>(G) : pick_attn<128>(G);
-  if (!f) {
-    set_error("attention: %d query heads per CTA not built (1,2,3,4,7,8 are)", G);
-    return B200_ERR_UNSUPPORTED;
-  }
-  const int chunk = (hd == 64) ? SplitKeys<64>::value : SplitKeys<128>::value;
-  const size_t smem = (size_t)2 * chunk * hd * 2 + (size_t)(G * hd + kAttnWarps * G * hd + G * chunk + 2 * G) * 4;
-  B200_CUDA(launch_pdl(f, dim3(p.nsplit, p.Hq / G), dim3(kAttnThreads), smem, st, pdl, p));
+  B200_CHECK_ARG(G >= 1 && G <= 8, "attention: at most 8 query heads per CTA (got %d)", G);
+  if (hd == 64)
+    B200_CUDA(launch_pdl(attn_decode_reg_kernel<64>, dim3(p.nsplit, p.Hq / G), dim3(kAttnThreads), 0, st, pdl, p, G));
+  else
+    B200_CUDA(launch_pdl(attn_decode_reg_kernel<128>, dim3(p.nsplit, p.Hq / G), dim3(kAttnThreads), 0, st, pdl, p, G));
   return B200_OK;
 }
 

@@ -64,11 +64,21 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t 
     set_error("cuTensorMapEncodeTiled is not available (no CUDA driver / device?)");
     return B200_ERR_NO_DEVICE;
   }
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  // box_cols > 256 bf16: describe the rows in 4- or 8-byte elements (inner box dimension ≤ 256 elements); the column
+  // coordinate the kernel passes is then in those elements (box index × 256 either way)
+  int epb = 1;  // bf16 per element
+  while (box_cols / epb > 256) epb *= 2;
+  if (epb > 4 || cols % epb != 0 || box_cols % epb != 0) {
+    set_error("tensor map: box of %d columns not expressible (cols=%lld)", box_cols, (long long)cols);
+    return B200_ERR_INVALID;
+  }
+  const CUtensorMapDataType dt = epb == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                 : epb == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT64;
+  cuuint64_t dims[2] = {(cuuint64_t)(cols / epb), (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
-  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)(box_cols / epb), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = enc(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

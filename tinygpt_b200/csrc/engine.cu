@@ -440,27 +440,25 @@ static int engine_build(const b200_model_desc* desc, const b200_weight_table* w,
   e->gen_count = (unsigned long long*)(e->arena + o_cnt);
   e->sample_ws = (void*)(e->arena + o_sample);
 
-  // ---- shared-memory budgets.  PDL keeps two consecutive kernels resident on an SM, and a kernel's TMA ring is
-  // filled while its predecessors still run; the deeper the ring, the more of a layer's weights are already on chip
-  // when the dependency resolves.  Budgets are what each GEMV could use, clipped so that every consecutive pair
-  // (qkv, attn, o, gate_up, down, qkv, …) fits in one SM.
-  const int kPair = 220 * 1024;
-  const int attn_smem = 2 * (d.head_dim == 64 ? 256 : 128) * d.head_dim * 2 + 40 * 1024;
+  // ---- shared-memory budgets = ring depth per GEMV.  Measured (B200, profiles/r02_ring_depth_sweep.txt): what decides
+  // the HBM-bound models is that EVERY kernel keeps ≈ 8 stages (128 KB per SM, 19 MB chip-wide) in flight — enough to
+  // cover the HBM latency at full bandwidth.  Round 1 split 220 KB between consecutive kernels so that PDL could keep
+  // both resident; that left down_proj / o_proj with 2–4 stages and they streamed at ≈ 4 TB/s (Mistral-7B 0.60–0.79 of
+  // the roofline depending on the box; 0.90 with 8 stages everywhere, Llama-3.2-3B 0.66 → 0.80, Qwen3-1.7B 0.61 →
+  // 0.65).  So: every GEMV gets what it wants up to 8 stages; kernels that want less (the small models' matrices fit
+  // whole) still co-reside and prefetch under PDL; the lm_head, alone at the end of the token, gets the maximum.
   const int nqkv_rows = e->qdim + 2 * e->kvdim;
-  int want_qkv = gemv_smem_wanted(nqkv_rows, d.hidden, 1, e->num_sms);
-  int want_o = gemv_smem_wanted(d.hidden, e->qdim, 1, e->num_sms);
-  int want_gu = gemv_smem_wanted(e->I_l, d.hidden, 2, e->num_sms);
-  int want_dn = gemv_smem_wanted(d.hidden, e->I_l, 1, e->num_sms);
-  int b_qkv = std::min(want_qkv, kPair - attn_smem);
-  int b_o = std::min(want_o, kPair - attn_smem);
-  int b_gu = want_gu, b_dn = want_dn;
-  if (b_gu + b_dn > kPair) {  // split what the pair has in proportion to what each wants
-    b_gu = (int)((int64_t)kPair * want_gu / (want_gu + want_dn));
-    b_dn = kPair - b_gu;
-  }
-  b_gu = std::min(b_gu, kPair - b_o);
-  b_dn = std::min(b_dn, kPair - b_qkv);
-  const int b_head = std::min(kGemvMaxSmem, kPair - b_dn);
+  const int kStages = env_int("B200_GEMV_RING", 8, 2, 13);
+  auto budget = [&](int64_t n, int64_t k, int nseg) {
+    const int64_t k_pad = (k + 1023) / 1024 * 1024;
+    const int cap = kStages * (16 * 1024 + 16) + (int)k_pad * 2 + 64;
+    return std::min(gemv_smem_wanted(n, k, nseg, e->num_sms), std::min(cap, kGemvMaxSmem));
+  };
+  int b_qkv = budget(nqkv_rows, d.hidden, 1);
+  int b_o = budget(d.hidden, e->qdim, 1);
+  int b_gu = budget(e->I_l, d.hidden, 2);
+  int b_dn = budget(d.hidden, e->I_l, 1);
+  const int b_head = kGemvMaxSmem;
   if (std::getenv("B200_UNIFORM_SMEM")) b_qkv = b_o = b_gu = b_dn = kGemvDefaultSmem;
 
   // ---- GEMV plans (TMA descriptors are encoded once, here).

@@ -94,12 +94,11 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
           mbar_wait(&empty[s], ph);
           mbar_arrive_expect_tx(&full[s], kStageBytes);
           uint8_t* dst = stage_base + (size_t)s * kStageBytes;
+          // one box per segment: kBoxR rows × (KB · 256) columns = KB · 512 contiguous bytes per row (the tensor map
+          // describes W in 2/4/8-byte elements so that the inner box dimension stays ≤ 256, gemv_make_plan)
 #pragma unroll
-          for (int kb = 0; kb < KB; ++kb)
-#pragma unroll
-            for (int seg = 0; seg < NSEG; ++seg)
-              tma_load_2d(dst + (kb * NSEG + seg) * kBoxBytes, &tmap, (ks * KB + kb) * kBoxK,
-                          seg * p.seg_rows + row0, &full[s]);
+          for (int seg = 0; seg < NSEG; ++seg)
+            tma_load_2d(dst + seg * (KB * kBoxBytes), &tmap, ks * kBoxK, seg * p.seg_rows + row0, &full[s]);
           if (++s == p.stages) {
             s = 0;
             ph ^= 1;
@@ -270,7 +269,7 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
   // ---------------------------------------------------------------------------------------------- main k loop
   int s = 0;
   uint32_t ph = 0;
-  const uint8_t* const my_rows = stage_base + (size_t)(warp * RPW) * kRowBytes + lane * 16;
+  const uint8_t* const my_rows = stage_base + (size_t)(warp * RPW) * (KB * kRowBytes) + lane * 16;
   for (int i = 0; i < my_rbs; ++i) {
     const int row_base = ((int)blockIdx.x + i * (int)gridDim.x) * kBoxR + warp * RPW;
     // operands of the epilogue are requested now so that their latency hides behind the k loop
@@ -303,7 +302,7 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
         for (int seg = 0; seg < NSEG; ++seg)
 #pragma unroll
           for (int r = 0; r < RPW; ++r)
-            wv[kb][seg][r] = *reinterpret_cast<const uint4*>(st + (kb * NSEG + seg) * kBoxBytes + r * kRowBytes);
+            wv[kb][seg][r] = *reinterpret_cast<const uint4*>(st + seg * (KB * kBoxBytes) + r * (KB * kRowBytes) + kb * kRowBytes);
 #pragma unroll
       for (int kb = 0; kb < KB; ++kb) {
         float xf[8];
@@ -504,7 +503,10 @@ int gemv_make_plan(GemvPlan* plan, const void* W, int64_t rows_total, int64_t n,
   B200_CHECK_ARG(pick(sh.rpw, nseg, pro, epi) != nullptr, "gemv: no kernel for nseg=%d pro=%d epi=%d", nseg, pro, epi);
   B200_CHECK_ARG(plan->smem <= kGemvMaxSmem + 4096, "gemv: k=%lld needs %d bytes of shared memory", (long long)k,
                  plan->smem);
-  return make_tmap_2d_bf16(&plan->tmap, W, rows_total, k, sh.box_r, kBoxK);
+  // one box = box_r rows × kb·256 columns: kb·512 contiguous bytes per row instead of kb separate 512-byte boxes (HBM
+  // sees 2 KB runs for one-row-per-warp kernels).  The inner box dimension is limited to 256 ELEMENTS, so W is described
+  // in 2·kb-byte elements (TMA only moves bytes; out-of-bounds columns are zero-filled whatever the element type).
+  return make_tmap_2d_bf16(&plan->tmap, W, rows_total, k, sh.box_r, kBoxK * sh.kb);
 }
 
 int gemv_launch(const GemvPlan& plan, cudaStream_t stream, bool pdl) {

@@ -60,7 +60,7 @@ struct GemvPlan {
 // `smem_budget` bounds the dynamic shared memory of the launch (ring depth): consecutive PDL-chained kernels co-reside
 // on an SM, so the engine hands out budgets whose pairwise sums fit in 227 KB (gemv_smem_wanted tells how much a
 // kernel could use to hold ALL of its busiest CTA's weights).
-constexpr int kGemvDefaultSmem = 100 * 1024;
+constexpr int kGemvDefaultSmem = 144 * 1024;  // 8 stages + the activation vector: the ring depth that saturates HBM
 constexpr int kGemvMaxSmem = 200 * 1024;
 int gemv_make_plan(GemvPlan* plan, const void* W, int64_t rows_total, int64_t n, int64_t k, int nseg, int pro, int epi,
                    int num_sms, int smem_budget = kGemvDefaultSmem);

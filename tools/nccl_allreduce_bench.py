@@ -53,8 +53,10 @@ def main():
         print("| model | H | dtype | all-reduces / token | us each | us / token |")
         print("|---|---|---|---|---|---|")
         for r in rows:
-            print(f"| {r[0]} | {r[1]} | {r[2]} | {r[3]} | {r[4]:.2f} | {r[5]:.0f} |")
-    dist.destroy_process_group()
+            print(f"| {r[0]} | {r[1]} | {r[2]} | {r[3]} | {r[4]:.2f} | {r[5]:.0f} |", flush=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    os._exit(0)   # tearing down a process group that holds captured NCCL graphs can block; everything is printed
 
 
 if __name__ == "__main__":
