@@ -147,7 +147,7 @@ int b200_attn_decode_bf16(void* out, const void* qkv, const void* q_norm_or_null
  * inverse-CDF draw with the caller's uniform number u in (0, 1]), without sorting the vocabulary (sampling.cu).
  * [ref: src/engine/Sampler.cpp:31-78; third_party/TinyTorch/src/Operation/OpSamplingCuda.cu:30-62,97-170,261-330]
  * Greedy decoding (temperature 0, top_k 0, top_p 1, min_p 0) is b200_argmax_bf16.  `workspace`: 256-byte aligned,
- * b200_sample_workspace_bytes() bytes.  Staged: modelled on the CPU, not yet run on hardware. */
+ * b200_sample_workspace_bytes() bytes. */
 int64_t b200_sample_workspace_bytes(void);
 int b200_sample_bf16(int64_t* token_out, const void* logits, int64_t V, float temperature, int64_t top_k, float top_p,
                      float min_p, float u, void* workspace, void* stream);
@@ -243,7 +243,7 @@ int b200_engine_set_mailbox(b200_engine* eng, uint64_t* ring_host_mapped, int64_
 /* SamplerConfig of the generate loop [ref: src/engine/Sampler.h:13-22, Sampler.cpp:14-21]: with any knob set
  * (temperature > 0, top_k > 0, top_p < 1, min_p > 0) the engine picks every token with the device sampler
  * (b200_sample_bf16's kernels, uniform number = Philox4x32-10(seed, tokens generated so far)); all knobs off = greedy
- * argmax again.  Re-captures the per-token graph; single-GPU engines only.  Staged. */
+ * argmax again.  Re-captures the per-token graph; single-GPU engines only. */
 int b200_engine_set_sampler(b200_engine* eng, float temperature, int64_t top_k, float top_p, float min_p, uint64_t seed,
                             void* stream);
 /* Host-side mirror: how many tokens this engine has generated (= n of the most recently enqueued token). */

@@ -54,7 +54,8 @@ struct b200_engine {
   // host mirrors
   int64_t h_pos = 0;
   int64_t h_gen = 0;
-  int launches_per_token = 0;
+  int launches_per_token = 0;   // kernels of a head token (what the graph g_step launches)
+  int launches_body = 0;        // kernels of a body-only token (g_body)
   // batched prefill (tcgen05 GEMM path), workspace allocated on first use
   uint8_t* pf_arena = nullptr;
   int pf_chunk = 0;  // tokens the workspace holds
@@ -285,6 +286,7 @@ static int engine_capture(b200_engine* e, bool with_head, cudaGraphExec_t* out) 
     return rc;
   }
   if (with_head) e->launches_per_token = (int)n;
+  else e->launches_body = (int)n;
   err = cudaGraphInstantiate(out, g, 0);
   cudaGraphDestroy(g);
   cudaStreamDestroy(st);
@@ -299,7 +301,7 @@ static int engine_run_token(b200_engine* e, cudaStream_t st, bool with_head) {
   if (e->use_graph) {
     cudaGraphExec_t g = with_head ? e->g_step : e->g_body;
     B200_CUDA(cudaGraphLaunch(g, st));
-    g_launches.fetch_add(with_head ? e->launches_per_token : e->launches_per_token - 2);
+    g_launches.fetch_add(with_head ? e->launches_per_token : e->launches_body);
     return B200_OK;
   }
   return engine_launch_token(e, st, with_head);

@@ -336,6 +336,23 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
       }
     }
     const int row = row_base + lane;
+    if constexpr (EPI == EPI_TP_PUSH && RPW > 1) {
+      // after the xor-shuffle trees every lane holds all RPW row sums: lane q serves peer q and stores the warp's RPW
+      // adjacent {value, tag} words as 16-byte vectors (RPW/2 NVLink writes per peer and warp instead of RPW 8-byte
+      // ones issued one peer after the other by RPW lanes)
+      if (row_base + RPW <= p.n) {
+        if (lane < p.tp_world) {
+          uint2* dst = p.tp_push[lane] + row_base;
+#pragma unroll
+          for (int r = 0; r < RPW; r += 2)
+            asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst + r), "r"(__float_as_uint(acc[0][r])),
+                         "r"(tp_tag), "r"(__float_as_uint(acc[0][r + 1])), "r"(tp_tag)
+                         : "memory");
+        }
+        if (tracing) p.trace[i == 0 ? 6 : 7] = (unsigned long long)(clock64() - c0);
+        continue;
+      }
+    }
     if (lane < RPW && row < p.n) {
       if constexpr (EPI == EPI_PLAIN) {
         __nv_bfloat16 v = f_to_bf16(a0);

@@ -1,7 +1,13 @@
 // sampling.cu — temperature / top-k / top-p / min-p sampling of one token from bf16 logits, on the device, WITHOUT
-// sorting the vocabulary.  Staged: written and modelled on the CPU
-// (tests/test_sampler_bins_model.py restates this exact plan in numpy against the pinned oracle), not yet run on
-// hardware.  Stand-alone op behind b200_sample_bf16; the engine still publishes the greedy token.
+// sorting the vocabulary.  Stand-alone op behind b200_sample_bf16 and, through
+// b200_engine_set_sampler, the last kernels of a token when any sampler knob is set.  On hardware: drawn index equal to
+// the pinned sampler oracle over 10 configurations × 5 uniform numbers × 4 vocabularies, deterministic, and every token
+// an engine draws replayable on the host (tests/test_async_sampler_gpu.py).
+// Parity target: the reference's Sampler arithmetic in fp32 (its CPU path, oracle/sampler_oracle.py pinned against the
+// reference's own Sampler.cpp).  The reference's CUDA path runs the same pipeline in the logits' dtype (bf16 divide,
+// softmax and cumsum, src/engine/Sampler.cpp:36-55) and leaves equal logits at a cut to thrust's unstable sort: a
+// top-p / min-p boundary can differ by an entry from it.  The uniform number is Philox(seed, tokens this ENGINE has
+// generated so far): two generate calls on one engine continue the stream, like the reference's global generator.
 //
 // Replaces tinygpt::Sampler::sample + multinomial  [ref: src/engine/Sampler.cpp:23-78;
 //   third_party/TinyTorch/src/Operation/OpSamplingCuda.cu:30-62 (inverse-CDF draw), :97-170 (topk = full thrust sort),

@@ -71,11 +71,17 @@ def load_model_config(path: str | Path, max_ctx: Optional[int] = None) -> models
         raise LoaderError("config.json: head_dim missing for qwen3")
     scaling = None
     if mt == "llama" and isinstance(doc.get("rope_scaling"), dict):
+        # The reference applies the llama3 formula to EVERY llama config that carries a rope_scaling object, whatever its
+        # rope_type (ModelConfig.cpp:79-88 parses the four numbers, ModelLlama.h:21-25,42 always passes them on).  Other
+        # rope types (linear, dynamic, yarn) would silently get llama3 arithmetic there; here they are refused.
         rs = doc["rope_scaling"]
-        if rs.get("rope_type", "") == "llama3":
-            scaling = models.RopeScaling(float(rs.get("factor", 1.0)), float(rs.get("high_freq_factor", 1.0)),
-                                         float(rs.get("low_freq_factor", 1.0)),
-                                         int(rs.get("original_max_position_embeddings", -1)))
+        rt = rs.get("rope_type", rs.get("type", "llama3"))
+        if rt != "llama3":
+            raise LoaderError(f"config.json: rope_scaling.rope_type {rt!r}: only llama3 scaling is built "
+                              "(the reference would apply the llama3 formula to it)")
+        scaling = models.RopeScaling(float(rs.get("factor", 1.0)), float(rs.get("high_freq_factor", 1.0)),
+                                     float(rs.get("low_freq_factor", 1.0)),
+                                     int(rs.get("original_max_position_embeddings", -1)))
     theta_default = 1.0 if mt == "llama" else 10000.0
     ctx = int(max_ctx if max_ctx is not None else doc.get("max_position_embeddings", 4096))
     return models.ModelSpec(

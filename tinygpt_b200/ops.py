@@ -188,7 +188,7 @@ def attn_decode(qkv, kcache, vcache, *, q_heads, kv_heads, head_dim, pos=None, f
 def sample(logits: torch.Tensor, temperature: float, top_k: int = 0, top_p: float = 1.0, min_p: float = 0.0,
            u: float = 0.5) -> torch.Tensor:
     """Sampler::sample for one row of bf16 logits [V] with the uniform number u supplied by the caller
-    [ref: src/engine/Sampler.cpp:31-78].  Returns an int64 device tensor [1].  Staged."""
+    [ref: src/engine/Sampler.cpp:31-78].  Returns an int64 device tensor [1]."""
     logits = _chk(logits, "sample.logits").view(-1)
     ws = torch.empty(lib().b200_sample_workspace_bytes(), dtype=torch.uint8, device=logits.device)
     out = torch.empty(1, dtype=torch.int64, device=logits.device)
