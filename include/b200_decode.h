@@ -215,19 +215,24 @@ int b200_engine_reset(b200_engine* eng, void* stream);
  * overwritten as decoding continues.  Used to re-decode from a shared prefix (and by bench.py between timed steps). */
 int b200_engine_seek(b200_engine* eng, int64_t position, void* stream);
 
-/* model()(ids): run S tokens (B must be 1) at the current position and return logits.
- *   logits_mode 0: logits_out is [1, V]   — last position only
- *   logits_mode 1: logits_out is [S, V]   — every position, like the reference's lm_head over all S
+/* model()(ids): run S tokens of B sequences (ids [B, S] row-major, 1 ≤ B ≤ 8, all at the engine's current position — the
+ * reference's left-padded batch, src/engine/GPTEngine.cpp:101-174) and return logits.
+ *   logits_mode 0: logits_out is [B, V]      — last position only
+ *   logits_mode 1: logits_out is [B, S, V]   — every position, like the reference's lm_head over all S
+ * B > 1 (single-GPU, greedy engines): every sequence has its own KV cache; a decode step streams the weights ONCE for the
+ * whole batch (gemv_batch.cu) and reproduces B independent batch-1 steps bit for bit.  The first call with a new B builds
+ * the batch's buffers and graphs.  b200_engine_decode / b200_engine_last_token follow the batch of the latest forward.
  * After the call the engine's "current token" is the greedy argmax of the last position (reference tie rule), so
  * b200_engine_decode can continue without a host round trip.  logits_out may be NULL. */
 int b200_engine_forward(b200_engine* eng, const int64_t* ids, int64_t B, int64_t S, void* logits_out,
                         int logits_mode, void* stream);
 
 /* The generateSync hot loop on device: n_steps × { forward(current token) → greedy argmax → becomes current }.
- * tokens_out[i] (int64) receives the token produced by step i.  No host synchronisation. */
+ * tokens_out[i] (int64) receives the token produced by step i ([n_steps][B] after a batched forward).  No host
+ * synchronisation. */
 int b200_engine_decode(b200_engine* eng, int64_t n_steps, int64_t* tokens_out, void* stream);
 
-/* Greedy token chosen after the most recent forward/decode step (int64, device → device copy on `stream`). */
+/* Greedy token(s) chosen after the most recent forward/decode step (int64 [B], device → device copy on `stream`). */
 int b200_engine_last_token(b200_engine* eng, int64_t* token_out, void* stream);
 
 /* Async token pipeline [ref: src/engine/GPTEngine.cpp:17-35 AsyncTokenPipeline / DefaultTokenPipeline::fetchTokenId —

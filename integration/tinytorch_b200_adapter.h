@@ -143,10 +143,9 @@ inline void registerOps() {
 }
 
 // ------------------------------------------------------------------------------------- boundary A: whole token
-// A Module that owns one b200_engine PER SEQUENCE of the batch, built from the weights the reference's loader already
-// placed on the device.  The engines borrow the same weights; each owns only its KV cache + workspace, so a batch of B
-// left-padded prompts (GPTEngine::generateSync, src/engine/GPTEngine.cpp:154-174) costs B caches and — for now — B
-// sequential weight passes per step (the engine is batch-1; SURVEY §8 scopes the path to batch 1).
+// A Module that owns ONE b200_engine built from the weights the reference's loader already placed on the device.  A
+// batch of B ≤ 8 left-padded prompts (GPTEngine::generateSync, src/engine/GPTEngine.cpp:154-174) goes through the
+// engine's batched step: B KV caches, ONE weight pass per decode step (b200_engine_forward with B > 1).
 class B200CausalLM : public tt::nn::Module {
  public:
   // `loaded` is the reference model after ModelLoader::load (src/huggingface/ModelLoader.cpp:25-87).
@@ -199,18 +198,26 @@ class B200CausalLM : public tt::nn::Module {
     ASSERT(ids.dim() == 2 && ids.dtype() == tt::DType::Int64);
     void* stream = currentStream(ids);
     const int64_t B = ids.shape(0), S = ids.shape(1), V = desc_.vocab;
-    while ((int64_t)engines_.size() < B) {
+    if (engines_.empty()) {
       b200_engine* e = nullptr;
       check(b200_engine_create(&desc_, &table_, &e), "b200_engine_create");
       engines_.push_back(e);
     }
     const bool fresh = S > 1 || (refCache_ != nullptr && refCache_->pastLength(0, 1) == 0);
     tt::Tensor logits = tt::Tensor::empty({B, S, V}, tt::Options(ids.device(), tt::DType::BFloat16).noGrad());
-    for (int64_t b = 0; b < B; ++b) {
-      if (fresh) check(b200_engine_reset(engines_[b], stream), "b200_engine_reset");
-      auto* last = logits.dataPtr<tt::BFloat16>() + (b * S + (S - 1)) * V;
-      check(b200_engine_forward(engines_[b], ids.dataPtr<int64_t>() + b * S, 1, S, last, /*logits_mode=*/0, stream),
+    if (fresh) check(b200_engine_reset(engines_[0], stream), "b200_engine_reset");
+    if (S == 1) {   // decode step: [B, 1, V] is exactly the engine's last-position layout
+      check(b200_engine_forward(engines_[0], ids.dataPtr<int64_t>(), B, 1, logits.dataPtr<tt::BFloat16>(), /*logits_mode=*/0,
+                                stream),
             "b200_engine_forward");
+    } else {        // prompt: only the last row of every sequence is computed (genNextToken narrows to it)
+      tt::Tensor last = tt::Tensor::empty({B, V}, tt::Options(ids.device(), tt::DType::BFloat16).noGrad());
+      check(b200_engine_forward(engines_[0], ids.dataPtr<int64_t>(), B, S, last.dataPtr<tt::BFloat16>(), /*logits_mode=*/0,
+                                stream),
+            "b200_engine_forward");
+      for (int64_t b = 0; b < B; ++b)
+        cudaMemcpyAsync(logits.dataPtr<tt::BFloat16>() + (b * S + (S - 1)) * V, last.dataPtr<tt::BFloat16>() + b * V,
+                        sizeof(tt::BFloat16) * V, cudaMemcpyDeviceToDevice, reinterpret_cast<cudaStream_t>(stream));
     }
     if (fresh && refCache_ != nullptr) {  // leave a mark so that the next resetCache() can be told from a decode step
       tt::Tensor mark = tt::Tensor::empty({1, 1, 1, 1}, tt::Options(ids.device(), tt::DType::BFloat16).noGrad());

@@ -7,7 +7,10 @@
 //   ref_cuda_decode --ckpt DIR --family {llama|qwen2|qwen3|mistral} --dims H,L,Hq,Hkv,hd,I,V,ctx --theta T --eps E
 //                   --tie {0|1} [--rope-scaling f,hi,lo,orig] --ids FILE(int64) --new N [--forced FILE(int64)]
 //                   --out FILE [--time-steps K] [--b200 {off|ops|engine}] [--qkv-bias 0|1] [--qk-norm 0|1]
-//                   [--dump-rope FILE] [--batched 1]
+//                   [--dump-rope FILE] [--batched 1] [--batch B]
+// --batch B: the ids file holds B equally long prompts (row-major [B, S]); every step runs the model on [B, n] ids like
+// GPTEngine::generateSync does for its left-padded batch (src/engine/GPTEngine.cpp:154-174).  Output: int64 [N][B]
+// tokens, then float32 [N][B][V] logits.  (--forced then holds [N][B] tokens.)
 // --dump-rope writes the fp32 cos/sin table of a RoPE module built as the family's createModel() builds it.
 // --batched 1 (needs --forced): ONE forward over prompt + forced tokens — the reference's batched path (cuBLAS GEMM with
 // m = S + N - 1, causal TinyFA) — and the logits of the same N positions: the reference against ITSELF through two of
@@ -91,7 +94,7 @@ int main(int argc, char** argv) {
   float theta = 10000.f, eps = 1e-5f;
   int tie = 1, nNew = 8, timeSteps = 0, qkvBias = -1, qkNorm = -1;
   std::string b200Mode = "off", ropeDump;
-  int batched = 0;
+  int batched = 0, batch = 1;
   for (int i = 1; i + 1 < argc; i += 2) {
     const std::string a = argv[i];
     const char* v = argv[i + 1];
@@ -112,6 +115,7 @@ int main(int argc, char** argv) {
     else if (a == "--qk-norm") qkNorm = atoi(v);
     else if (a == "--dump-rope") ropeDump = v;
     else if (a == "--batched") batched = atoi(v);
+    else if (a == "--batch") batch = atoi(v);
   }
   if (ckpt.empty() || dims.size() != 8 || idsPath.empty() || outPath.empty()) {
     fprintf(stderr, "usage: see the header of oracle/ref_cuda_main.cpp\n");
@@ -207,12 +211,65 @@ int main(int argc, char** argv) {
 
   const std::vector<int64_t> ids = readI64(idsPath);
   const std::vector<int64_t> forced = forcedPath.empty() ? std::vector<int64_t>() : readI64(forcedPath);
-  if (ids.empty() || (!forcedPath.empty() && (int)forced.size() < nNew)) {
+  if (ids.empty() || ids.size() % batch != 0 || (!forcedPath.empty() && (int)forced.size() < nNew * batch)) {
     fprintf(stderr, "bad --ids / --forced\n");
     return 2;
   }
   const int64_t V = (int64_t)dims[6];
-  const int64_t S = (int64_t)ids.size();
+  const int64_t S = (int64_t)ids.size() / batch;
+  if (batch > 1) {
+    // batch of equally long prompts: [B, S] ids per step, every sequence's last-position logits and greedy token
+    auto idsB = [&](const int64_t* p, int64_t n) {
+      tt::Tensor t = tt::Tensor::empty({(int64_t)batch, n}, tt::Options(tt::Device(tt::DeviceType::CPU), tt::DType::Int64));
+      std::memcpy(t.dataPtr<int64_t>(), p, sizeof(int64_t) * batch * n);
+      return t.to(dev);
+    };
+    std::vector<int64_t> toksB;
+    std::vector<float> logB((size_t)nNew * batch * V);
+    std::vector<int64_t> cur(batch);
+    auto stepB = [&](const tt::Tensor& in, int64_t n, int k) {
+      tt::Tensor logits = model->forward(in);                                         // [B, n, V]
+      tt::Tensor last = tt::function::narrow(logits, 1, n - 1, 1).squeeze(1);         // [B, V]
+      tt::Tensor next = tt::function::argmax(last, -1, true).to(tt::Device(tt::DeviceType::CPU));
+      tt::Tensor f = last.to(tt::DType::Float32).to(tt::Device(tt::DeviceType::CPU));
+      std::memcpy(logB.data() + (size_t)k * batch * V, f.dataPtr<float>(), sizeof(float) * batch * V);
+      for (int b = 0; b < batch; ++b) {
+        cur[b] = next.dataPtr<int64_t>()[b];
+        toksB.push_back(cur[b]);
+      }
+    };
+    model->resetCache();
+    stepB(idsB(ids.data(), S), S, 0);
+    for (int k = 1; k < nNew; ++k) {
+      std::vector<int64_t> in(cur);
+      if (!forced.empty())
+        for (int b = 0; b < batch; ++b) in[b] = forced[(size_t)(k - 1) * batch + b];
+      stepB(idsB(in.data(), 1), 1, k);
+    }
+    FILE* fb = fopen(outPath.c_str(), "wb");
+    if (!fb) return 4;
+    fwrite(toksB.data(), 8, toksB.size(), fb);
+    fwrite(logB.data(), 4, logB.size(), fb);
+    fclose(fb);
+    if (timeSteps > 0) {
+      model->resetCache();
+      tt::Tensor curT = tt::function::argmax(
+          tt::function::narrow(model->forward(idsB(ids.data(), S)), 1, S - 1, 1).squeeze(1), -1, true);   // [B, 1]
+      cudaDeviceSynchronize();
+      const auto t0 = std::chrono::steady_clock::now();
+      for (int k = 0; k < timeSteps; ++k) {
+        tt::Tensor logits = model->forward(curT);
+        curT = tt::function::argmax(tt::function::narrow(logits, 1, 0, 1).squeeze(1), -1, true);
+      }
+      cudaDeviceSynchronize();
+      const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      printf("{\"impl\": \"reference-cuda\", \"b200\": \"%s\", \"batch\": %d, \"tokens_per_s\": %.3f, \"us_per_step\": %.2f, "
+             "\"steps\": %d, \"prompt\": %lld}\n",
+             b200Mode.c_str(), batch, timeSteps * batch / dt, dt / timeSteps * 1e6, timeSteps, (long long)S);
+    }
+    fflush(stdout);
+    _exit(0);
+  }
   auto idsTensor = [&](const int64_t* p, int64_t n) {
     tt::Tensor t = tt::Tensor::empty({1, n}, tt::Options(tt::Device(tt::DeviceType::CPU), tt::DType::Int64));
     std::memcpy(t.dataPtr<int64_t>(), p, sizeof(int64_t) * n);

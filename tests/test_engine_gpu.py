@@ -136,7 +136,7 @@ def test_engine_state_and_errors(built_lib):
     with pytest.raises(B200Error):
         eng.decode(64)  # context overflow is an error, not a silent wrap
     with pytest.raises(B200Error):
-        eng.forward(torch.zeros(2, 3, dtype=torch.int64, device=DEV))  # batch-1 engine
+        eng.forward(torch.zeros(9, 3, dtype=torch.int64, device=DEV))  # at most 8 sequences per batched step
     with pytest.raises(B200Error):
         eng.forward(torch.zeros(1, 3, dtype=torch.int32, device=DEV))
     host = eng.generate_sync([1, 2, 3, 4], 6)

@@ -21,7 +21,7 @@ LIB_DIR = PKG / "lib"
 OBJ_DIR = LIB_DIR / "obj"
 LIB_PATH = LIB_DIR / "libb200decode.so"
 
-SOURCES = ["common.cu", "gemv.cu", "gemm.cu", "prefill.cu", "prefill_attn.cu", "sampling.cu", "ops.cu", "attn.cu", "engine.cu", "api.cu", "tp.cu"]
+SOURCES = ["common.cu", "gemv.cu", "gemv_batch.cu", "gemm.cu", "prefill.cu", "prefill_attn.cu", "sampling.cu", "ops.cu", "attn.cu", "engine.cu", "api.cu", "tp.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -57,7 +57,7 @@ struct SplitKeys {
 //     8 warps through 5 KB of shared memory: two more barriers per query head, none for scores / softmax / P·V.
 // The new K/V row is written in place to the cache and handed to the owning thread through shared memory.
 template <int HD>
-__global__ void __launch_bounds__(kAttnThreads) attn_decode_reg_kernel(const AttnDecodeParams p, const int G) {
+__global__ void __launch_bounds__(kAttnThreads) attn_decode_reg_kernel(const AttnDecodeParams p_in, const int G) {
   constexpr int LPK = HD / 8;             // lanes per key row
   constexpr int NG = kAttnThreads / LPK;  // key rows per pass
   constexpr int KPT = 8;                  // key rows per thread
@@ -73,11 +73,21 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_reg_kernel(const Att
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int hg = blockIdx.y, split = blockIdx.x;
+  AttnDecodeParams p = p_in;
+  {  // batched decode: this CTA's sequence
+    const long long b = blockIdx.z;
+    p.qkv += b * p.qkv_bstride;
+    p.out += b * p.out_bstride;
+    p.kcache += b * p.cache_bstride;
+    p.vcache += b * p.cache_bstride;
+    p.ws += b * p.ws_bstride;
+    p.tickets += b * p.tick_bstride;
+  }
   const int h0 = hg * G;
   const int group = p.Hq / p.Hkv;
   const int kvh = h0 / group;
   const bool kv_leader = (h0 % group) == 0;
-  if (p.trace != nullptr && hg == 0 && split == 0 && tid == 0) p.trace[0] = global_timer_ns();
+  if (p.trace != nullptr && hg == 0 && split == 0 && blockIdx.z == 0 && tid == 0) p.trace[0] = global_timer_ns();
   pdl_trigger();
   const bool append = (p.pos != nullptr);
   const int pos = append ? *p.pos : p.fixed_len - 1;   // stable since before the producer kernel started (engine.cu)
@@ -379,10 +389,11 @@ int launch_attn_decode(const AttnDecodeParams& p, int hd, cudaStream_t st, bool 
                  attn_decode_nsplit(hd, p.max_ctx));
   B200_CHECK_ARG(p.nsplit <= 65535, "attention: context too long");
   B200_CHECK_ARG(G >= 1 && G <= 8, "attention: at most 8 query heads per CTA (got %d)", G);
+  const unsigned nb = (unsigned)std::max(1, p.batch);
   if (hd == 64)
-    B200_CUDA(launch_pdl(attn_decode_reg_kernel<64>, dim3(p.nsplit, p.Hq / G), dim3(kAttnThreads), 0, st, pdl, p, G));
+    B200_CUDA(launch_pdl(attn_decode_reg_kernel<64>, dim3(p.nsplit, p.Hq / G, nb), dim3(kAttnThreads), 0, st, pdl, p, G));
   else
-    B200_CUDA(launch_pdl(attn_decode_reg_kernel<128>, dim3(p.nsplit, p.Hq / G), dim3(kAttnThreads), 0, st, pdl, p, G));
+    B200_CUDA(launch_pdl(attn_decode_reg_kernel<128>, dim3(p.nsplit, p.Hq / G, nb), dim3(kAttnThreads), 0, st, pdl, p, G));
   return B200_OK;
 }
 

@@ -70,6 +70,25 @@ struct b200_engine {
   unsigned long long* tp_epoch = nullptr;          // tokens completed (local)
   __nv_bfloat16* x_alt = nullptr;                  // second hidden-state buffer (TP ping-pong)
   const __nv_bfloat16* x_head = nullptr;           // residual the lm_head prologue reads (TP)
+  // ---- batched decode (B ≤ 8 sequences at the same position, the reference's left-padded batch): own KV caches and
+  // activations for all B sequences, GEMV plans that stream W once for the batch (gemv_batch.cu), own graphs.  Built on
+  // the first forward with B > 1 (engine_batch_prepare).
+  int batch = 1;                       // sequences of the most recent forward (decode / last_token follow it)
+  int b_cap = 0;                       // batch the buffers / plans / graphs below were built for
+  uint8_t* b_arena = nullptr;
+  __nv_bfloat16 *bk = nullptr, *bv = nullptr;                 // [B][L][max_ctx][Hkv][hd]
+  __nv_bfloat16 *bx = nullptr, *bqkv = nullptr, *battn = nullptr, *bact = nullptr, *blogits = nullptr;   // [B][·]
+  float* b_attn_ws = nullptr;
+  unsigned int* b_tickets = nullptr;
+  void* b_argmax_ws = nullptr;
+  int64_t* b_tok = nullptr;            // [B] token every sequence consumes next
+  int64_t* b_log = nullptr;            // [gen_cap][B] generated tokens
+  unsigned long long* b_cnt = nullptr; // [B] tokens generated per sequence (all equal)
+  int64_t hb_gen = 0;                  // host mirror of b_cnt
+  std::vector<b200::GemvPlan> bp_qkv, bp_o, bp_gu, bp_down;
+  b200::GemvPlan bp_head{};
+  cudaGraphExec_t gb_step = nullptr, gb_body = nullptr;
+  int b_launches = 0, b_launches_body = 0;
   unsigned long long* trace = nullptr;  // B200_TRACE=1: [launch][8] globaltimer stamps of the last token
   bool use_graph = true;
   bool use_pdl = true;
@@ -87,6 +106,8 @@ struct b200_engine {
 
 namespace b200 {
 
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
 namespace {
 
 // embed: x = E[cur_tok]   (first kernel of every token)
@@ -95,10 +116,10 @@ __global__ void __launch_bounds__(128) embed_step_kernel(__nv_bfloat16* __restri
                                                          const int64_t* __restrict__ tok, int64_t V, int H) {
   pdl_trigger();
   pdl_wait();
-  int64_t id = *tok;
+  int64_t id = tok[blockIdx.x];   // one CTA per sequence of a batched step
   if (id < 0 || id >= V) id = 0;
   const uint4* s4 = reinterpret_cast<const uint4*>(table + id * H);
-  uint4* d4 = reinterpret_cast<uint4*>(x);
+  uint4* d4 = reinterpret_cast<uint4*>(x + (size_t)blockIdx.x * H);
   for (int i = threadIdx.x; i < (H >> 3); i += blockDim.x) d4[i] = s4[i];
 }
 
@@ -261,7 +282,9 @@ static int engine_launch_token(b200_engine* e, cudaStream_t st, bool with_head) 
   return B200_OK;
 }
 
-static int engine_capture(b200_engine* e, bool with_head, cudaGraphExec_t* out) {
+static int engine_launch_token_batch(b200_engine* e, cudaStream_t st, bool with_head);
+
+static int engine_capture(b200_engine* e, bool with_head, cudaGraphExec_t* out, bool batched = false) {
   cudaStream_t st;
   B200_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   cudaGraph_t g = nullptr;
@@ -272,7 +295,7 @@ static int engine_capture(b200_engine* e, bool with_head, cudaGraphExec_t* out) 
     return B200_ERR_CUDA;
   }
   const int64_t before = g_launches.load();
-  int rc = engine_launch_token(e, st, with_head);
+  int rc = batched ? engine_launch_token_batch(e, st, with_head) : engine_launch_token(e, st, with_head);
   const int64_t n = g_launches.load() - before;
   g_launches.fetch_sub(n);  // capture does not execute anything
   err = cudaStreamEndCapture(st, &g);
@@ -285,7 +308,8 @@ static int engine_capture(b200_engine* e, bool with_head, cudaGraphExec_t* out) 
     }
     return rc;
   }
-  if (with_head) e->launches_per_token = (int)n;
+  if (batched) (with_head ? e->b_launches : e->b_launches_body) = (int)n;
+  else if (with_head) e->launches_per_token = (int)n;
   else e->launches_body = (int)n;
   err = cudaGraphInstantiate(out, g, 0);
   cudaGraphDestroy(g);
@@ -295,6 +319,165 @@ static int engine_capture(b200_engine* e, bool with_head, cudaGraphExec_t* out) 
     return B200_ERR_CUDA;
   }
   return B200_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------- batched decode
+// B sequences at the same position [ref: GPTEngine::generateSync left-pads the prompts to one length and runs the model
+// on [B, S] ids, src/engine/GPTEngine.cpp:101-174; every Linear then sees m = B rows].  One graph per token: embed (B
+// CTAs) + L × {qkv, attention (grid.z = B), o_proj, gate|up, down} with the batched GEMV (W streamed once for all B) +
+// lm_head + argmax (B rows).
+static int engine_launch_token_batch(b200_engine* e, cudaStream_t st, bool with_head) {
+  const b200_model_desc& d = e->d;
+  const bool pdl = e->use_pdl;
+  const int B = e->b_cap;
+  int rc;
+  B200_CUDA(launch_pdl(embed_step_kernel, dim3(B), dim3(128), 0, st, false, e->bx, e->embed, (const int64_t*)e->b_tok,
+                       (int64_t)d.vocab, (int)d.hidden));
+  const size_t kv_layer = (size_t)d.max_ctx * e->Hkv_l * d.head_dim;
+  const int nqkv = e->qdim + 2 * e->kvdim;
+  for (int l = 0; l < d.layers; ++l) {
+    if ((rc = gemv_launch(e->bp_qkv[l], st, pdl)) != B200_OK) return rc;
+    AttnDecodeParams a{};
+    a.qkv = e->bqkv;
+    a.q_norm = (const __nv_bfloat16*)e->lw[l].q_norm;
+    a.k_norm = (const __nv_bfloat16*)e->lw[l].k_norm;
+    a.eps = d.rms_eps;
+    a.rope = e->rope;
+    a.pos = e->pos;
+    a.kcache = e->bk + (size_t)l * kv_layer;
+    a.vcache = e->bv + (size_t)l * kv_layer;
+    a.out = e->battn;
+    a.ws = e->b_attn_ws;
+    a.tickets = e->b_tickets;
+    a.Hq = e->Hq_l;
+    a.Hkv = e->Hkv_l;
+    a.nsplit = e->nsplit;
+    a.max_ctx = d.max_ctx;
+    a.batch = B;
+    a.qkv_bstride = nqkv;
+    a.out_bstride = e->qdim;
+    a.cache_bstride = (long long)d.layers * (long long)kv_layer;
+    a.ws_bstride = attn_decode_ws_floats(e->Hq_l, e->Hkv_l, d.head_dim, e->nsplit);
+    a.tick_bstride = e->Hq_l;
+    if ((rc = launch_attn_decode(a, d.head_dim, st, pdl)) != B200_OK) return rc;
+    if ((rc = gemv_launch(e->bp_o[l], st, pdl)) != B200_OK) return rc;
+    if ((rc = gemv_launch(e->bp_gu[l], st, pdl)) != B200_OK) return rc;
+    const bool last_node = !with_head && l == d.layers - 1;
+    GemvPlan dn = e->bp_down[l];
+    dn.p.pos_inc = last_node ? e->pos : nullptr;   // the LAST kernel of a token advances the position
+    if ((rc = gemv_launch(dn, st, pdl && !last_node)) != B200_OK) return rc;
+  }
+  if (with_head) {
+    if ((rc = gemv_launch(e->bp_head, st, pdl)) != B200_OK) return rc;
+    int64_t* amax = reinterpret_cast<int64_t*>((uint8_t*)e->b_argmax_ws + argmax_workspace_bytes(B, e->V_l));
+    ArgmaxPublish pub;
+    pub.pos = e->pos;
+    pub.cur_tok = e->b_tok;
+    pub.gen_log = e->b_log;
+    pub.gen_count = e->b_cnt;
+    pub.gen_cap = e->gen_cap;
+    pub.batch_rows = B;
+    if ((rc = launch_argmax(amax, e->blogits, B, e->V_l, e->b_argmax_ws, st, false, &pub)) != B200_OK) return rc;
+  }
+  return B200_OK;
+}
+
+static void engine_batch_free(b200_engine* e) {
+  if (e->gb_step) cudaGraphExecDestroy(e->gb_step);
+  if (e->gb_body) cudaGraphExecDestroy(e->gb_body);
+  if (e->b_arena) cudaFree(e->b_arena);
+  e->gb_step = e->gb_body = nullptr;
+  e->b_arena = nullptr;
+  e->b_cap = 0;
+}
+
+// Buffers, plans and graphs for a batch of B sequences (kept until a forward asks for another B).
+static int engine_batch_prepare(b200_engine* e, int B) {
+  if (e->b_cap == B) return B200_OK;
+  const b200_model_desc& d = e->d;
+  B200_CHECK_ARG(B >= 2 && B <= kMaxBatch, "engine_forward: batch %d not built (1 … %d sequences per step)", B, kMaxBatch);
+  if (e->tp_world > 1 || e->sampler_on || e->mailbox != nullptr) {
+    set_error("engine_forward: batched decode is single-GPU, greedy, without a token mailbox");
+    return B200_ERR_UNSUPPORTED;
+  }
+  int rc;
+  if ((rc = gemv_batch_setup_attributes()) != B200_OK) return rc;
+  B200_CUDA(cudaDeviceSynchronize());
+  engine_batch_free(e);
+  const size_t kv_layer = (size_t)d.max_ctx * e->Hkv_l * d.head_dim;
+  const size_t kv_bytes = (size_t)B * d.layers * kv_layer * 2;
+  const int nqkv = e->qdim + 2 * e->kvdim;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  };
+  const size_t o_k = take(kv_bytes), o_v = take(kv_bytes);
+  const size_t o_x = take((size_t)B * d.hidden * 2), o_qkv = take((size_t)B * nqkv * 2);
+  const size_t o_attn = take((size_t)B * e->qdim * 2), o_act = take((size_t)B * e->I_l * 2);
+  const size_t o_logits = take((size_t)B * e->V_l * 2);
+  const size_t ws_floats = (size_t)attn_decode_ws_floats(e->Hq_l, e->Hkv_l, d.head_dim, e->nsplit);
+  const size_t o_ws = take((size_t)B * ws_floats * 4), o_tick = take((size_t)B * e->Hq_l * 4);
+  const size_t o_amax = take((size_t)argmax_workspace_bytes(B, e->V_l) + (size_t)B * 8 + 16);
+  const size_t o_tok = take((size_t)B * 8), o_log = take((size_t)e->gen_cap * B * 8), o_cnt = take((size_t)B * 8);
+  B200_CUDA(cudaMalloc((void**)&e->b_arena, off));
+  B200_CUDA(cudaMemset(e->b_arena + o_x, 0, off - o_x));   // control + activations (KV rows are written before read)
+  e->bk = (__nv_bfloat16*)(e->b_arena + o_k);
+  e->bv = (__nv_bfloat16*)(e->b_arena + o_v);
+  e->bx = (__nv_bfloat16*)(e->b_arena + o_x);
+  e->bqkv = (__nv_bfloat16*)(e->b_arena + o_qkv);
+  e->battn = (__nv_bfloat16*)(e->b_arena + o_attn);
+  e->bact = (__nv_bfloat16*)(e->b_arena + o_act);
+  e->blogits = (__nv_bfloat16*)(e->b_arena + o_logits);
+  e->b_attn_ws = (float*)(e->b_arena + o_ws);
+  e->b_tickets = (unsigned int*)(e->b_arena + o_tick);
+  e->b_argmax_ws = (void*)(e->b_arena + o_amax);
+  e->b_tok = (int64_t*)(e->b_arena + o_tok);
+  e->b_log = (int64_t*)(e->b_arena + o_log);
+  e->b_cnt = (unsigned long long*)(e->b_arena + o_cnt);
+  e->hb_gen = 0;
+  e->b_cap = B;
+  // plans: the single-sequence plans (same tensor maps, shapes, ring rule) pointed at the batch buffers
+  e->bp_qkv = e->p_qkv;
+  e->bp_o = e->p_o;
+  e->bp_gu = e->p_gu;
+  e->bp_down = e->p_down;
+  e->bp_head = e->p_head;
+  for (int l = 0; l < d.layers; ++l) {
+    GemvPlan &q = e->bp_qkv[l], &o = e->bp_o[l], &g = e->bp_gu[l], &dn = e->bp_down[l];
+    q.p.x = e->bx;
+    q.p.y = e->bqkv;
+    o.p.x = e->battn;
+    o.p.residual = e->bx;
+    o.p.y = e->bx;
+    g.p.x = e->bx;
+    g.p.y = e->bact;
+    dn.p.x = e->bact;
+    dn.p.residual = e->bx;
+    dn.p.y = e->bx;
+    if ((rc = gemv_plan_set_batch(&q, B)) != B200_OK || (rc = gemv_plan_set_batch(&o, B)) != B200_OK ||
+        (rc = gemv_plan_set_batch(&g, B)) != B200_OK || (rc = gemv_plan_set_batch(&dn, B)) != B200_OK)
+      return rc;
+  }
+  e->bp_head.p.x = e->bx;
+  e->bp_head.p.y = e->blogits;
+  if ((rc = gemv_plan_set_batch(&e->bp_head, B)) != B200_OK) return rc;
+  if (e->use_graph) {
+    if ((rc = engine_capture(e, true, &e->gb_step, true)) != B200_OK) return rc;
+    if ((rc = engine_capture(e, false, &e->gb_body, true)) != B200_OK) return rc;
+  }
+  return B200_OK;
+}
+
+static int engine_run_token_batch(b200_engine* e, cudaStream_t st, bool with_head) {
+  if (e->use_graph) {
+    B200_CUDA(cudaGraphLaunch(with_head ? e->gb_step : e->gb_body, st));
+    g_launches.fetch_add(with_head ? e->b_launches : e->b_launches_body);
+    return B200_OK;
+  }
+  return engine_launch_token_batch(e, st, with_head);
 }
 
 static int engine_run_token(b200_engine* e, cudaStream_t st, bool with_head) {
@@ -307,7 +490,6 @@ static int engine_run_token(b200_engine* e, cudaStream_t st, bool with_head) {
   return engine_launch_token(e, st, with_head);
 }
 
-static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 static int engine_build(const b200_model_desc* desc, const b200_weight_table* w, void* const* windows,
                         b200_engine** out) {
@@ -691,6 +873,7 @@ void b200_engine_destroy(b200_engine* e) {
   if (e->arena) cudaFree(e->arena);
   if (e->pf_arena) cudaFree(e->pf_arena);
   if (e->trace) cudaFree(e->trace);
+  b200::engine_batch_free(e);
   delete e;
 }
 
@@ -721,8 +904,8 @@ int b200_engine_forward(b200_engine* e, const int64_t* ids, int64_t B, int64_t S
                         void* stream) {
   using namespace b200;
   B200_CHECK_ARG(e && ids, "engine_forward: null argument");
-  B200_CHECK_ARG(B == 1, "engine_forward: batch %lld not built (decode engine is batch-1; run sequences one by one)",
-                 (long long)B);
+  B200_CHECK_ARG(B >= 1 && B <= kMaxBatch, "engine_forward: batch %lld not built (1 … %d sequences per step)", (long long)B,
+                 kMaxBatch);
   B200_CHECK_ARG(S >= 1, "engine_forward: empty sequence");
   B200_CHECK_ARG(logits_mode == 0 || logits_mode == 1, "engine_forward: logits_mode must be 0 or 1");
   if (e->h_pos + S > e->d.max_ctx) {
@@ -732,6 +915,50 @@ int b200_engine_forward(b200_engine* e, const int64_t* ids, int64_t B, int64_t S
   }
   cudaStream_t st = (cudaStream_t)stream;
   const size_t vbytes = (size_t)e->V_l * 2;
+  if (B > 1) {
+    // ---- batch of B sequences at the same position (ids [B, S] row-major, logits [B, 1 or S, V])
+    int rc = engine_batch_prepare(e, (int)B);
+    if (rc != B200_OK) return rc;
+    e->batch = (int)B;
+    const size_t kv_seq = (size_t)e->d.layers * e->d.max_ctx * e->Hkv_l * e->d.head_dim;
+    if (e->use_prefill_gemm && logits_mode == 0 && S >= kPrefillMin) {
+      // prompts: the batch-1 tensor-core prefill, sequence by sequence, into that sequence's KV cache (prefill is
+      // compute-bound: nothing to share between sequences); it leaves the last-position logits and the greedy token
+      __nv_bfloat16 *k0 = e->kcache, *v0 = e->vcache;
+      for (int64_t b = 0; b < B; ++b) {
+        e->kcache = e->bk + (size_t)b * kv_seq;
+        e->vcache = e->bv + (size_t)b * kv_seq;
+        rc = engine_prefill(e, ids + b * S, S, st);
+        e->kcache = k0;
+        e->vcache = v0;
+        if (rc != B200_OK) return rc;
+        B200_CUDA(cudaMemcpyAsync(e->blogits + (size_t)b * e->V_l, e->logits, vbytes, cudaMemcpyDeviceToDevice, st));
+        B200_CUDA(cudaMemcpyAsync(e->b_tok + b, e->cur_tok, 8, cudaMemcpyDeviceToDevice, st));
+        e->h_gen += 1;   // the prefill's argmax appended to the single-sequence log
+      }
+      if (logits_out != nullptr)
+        B200_CUDA(cudaMemcpyAsync(logits_out, e->blogits, (size_t)B * vbytes, cudaMemcpyDeviceToDevice, st));
+      e->h_pos += S;
+      return B200_OK;
+    }
+    for (int64_t t = 0; t < S; ++t) {
+      // column t of ids → the B current tokens
+      B200_CUDA(cudaMemcpy2DAsync(e->b_tok, 8, ids + t, (size_t)S * 8, 8, (size_t)B, cudaMemcpyDeviceToDevice, st));
+      const bool head = (t == S - 1) || (logits_mode == 1 && logits_out != nullptr);
+      if ((rc = engine_run_token_batch(e, st, head)) != B200_OK) return rc;
+      if (head) e->hb_gen += 1;
+      if (head && logits_out != nullptr) {
+        if (logits_mode == 1)   // [B][S][V]: row t of every sequence
+          B200_CUDA(cudaMemcpy2DAsync((uint8_t*)logits_out + (size_t)t * vbytes, (size_t)S * vbytes, e->blogits, vbytes,
+                                      vbytes, (size_t)B, cudaMemcpyDeviceToDevice, st));
+        else
+          B200_CUDA(cudaMemcpyAsync(logits_out, e->blogits, (size_t)B * vbytes, cudaMemcpyDeviceToDevice, st));
+      }
+    }
+    e->h_pos += S;
+    return B200_OK;
+  }
+  e->batch = 1;
   if (e->use_prefill_gemm && e->tp_world == 1 && logits_mode == 0 && S >= kPrefillMin) {
     // batched prefill: every Linear of the prompt on the tcgen05 GEMM, lm_head for the last position only
     int rc = engine_prefill(e, ids, S, st);
@@ -766,6 +993,23 @@ int b200_engine_decode(b200_engine* e, int64_t n_steps, int64_t* tokens_out, voi
     return B200_ERR_STATE;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (e->batch > 1) {   // tokens_out [n_steps][B]
+    const int64_t B = e->batch, first_b = e->hb_gen;
+    for (int64_t i = 0; i < n_steps; ++i) {
+      int rc = engine_run_token_batch(e, st, true);
+      if (rc != B200_OK) return rc;
+    }
+    e->hb_gen += n_steps;
+    e->h_pos += n_steps;
+    if (tokens_out != nullptr && n_steps > 0) {
+      const int64_t a = first_b % e->gen_cap;
+      const int64_t n1 = std::min<int64_t>(n_steps, e->gen_cap - a);
+      B200_CUDA(cudaMemcpyAsync(tokens_out, e->b_log + a * B, (size_t)n1 * B * 8, cudaMemcpyDeviceToDevice, st));
+      if (n1 < n_steps)
+        B200_CUDA(cudaMemcpyAsync(tokens_out + n1 * B, e->b_log, (size_t)(n_steps - n1) * B * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    return B200_OK;
+  }
   const int64_t first = e->h_gen;
   for (int64_t i = 0; i < n_steps; ++i) {
     int rc = engine_run_token(e, st, true);
@@ -786,6 +1030,10 @@ int b200_engine_decode(b200_engine* e, int64_t n_steps, int64_t* tokens_out, voi
 int b200_engine_last_token(b200_engine* e, int64_t* token_out, void* stream) {
   using namespace b200;
   B200_CHECK_ARG(e && token_out, "engine_last_token: null argument");
+  if (e->batch > 1) {   // token_out [B]
+    B200_CUDA(cudaMemcpyAsync(token_out, e->b_tok, (size_t)e->batch * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return B200_OK;
+  }
   B200_CUDA(cudaMemcpyAsync(token_out, e->cur_tok, 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return B200_OK;
 }

@@ -29,18 +29,9 @@
 
 namespace b200 {
 
+using namespace gemvk;
+
 namespace {
-
-constexpr int kNW = 8;                      // consumer warps
-constexpr int kThreads = (kNW + 1) * 32;    // + 1 producer warp
-constexpr int kBoxK = 256;                  // columns per TMA box
-constexpr int kRowBytes = kBoxK * 2;        // 512
-constexpr int kConsumers = kNW * 32;
-constexpr int kMaxStages = 32;
-
-// 256-column TMA boxes per pipeline stage: every stage carries 16 KB (32 KB for RPW 4 × 2 segments) so that the
-// per-stage barrier traffic is amortised whatever the row-block height.
-__host__ __device__ constexpr int kboxes(int rpw, int nseg) { return (4 / (rpw * nseg)) > 0 ? 4 / (rpw * nseg) : 1; }
 
 __device__ __forceinline__ uint4 ld_volatile_u4(const uint4* p) {
   uint4 v;
@@ -526,7 +517,30 @@ int gemv_make_plan(GemvPlan* plan, const void* W, int64_t rows_total, int64_t n,
   return make_tmap_2d_bf16(&plan->tmap, W, rows_total, k, sh.box_r, kBoxK * sh.kb);
 }
 
+int gemv_plan_set_batch(GemvPlan* plan, int B) {
+  B200_CHECK_ARG(B >= 1 && B <= kMaxBatch, "gemv: batch %d out of range (1 … %d)", B, kMaxBatch);
+  B200_CHECK_ARG((plan->pro == PRO_PLAIN || plan->pro == PRO_RMSNORM) && plan->epi != EPI_TP_PUSH,
+                 "gemv: batched decode is single-GPU only");
+  plan->batch = B;
+  plan->p.batch = B;
+  plan->p.x_stride = plan->p.k;
+  plan->p.y_stride = plan->p.n;
+  if (B == 1) return B200_OK;
+  const int mb = B <= 2 ? 2 : B <= 4 ? 4 : 8;
+  const int kb = kboxes(plan->rpw, plan->nseg);
+  const int stage_bytes = kb * plan->nseg * 8 * plan->rpw * kRowBytes;
+  const int fixed = mb * plan->p.k_pad * 2 + 64 + mb * kNW * 4;
+  int stages = plan->p.stages;
+  while (stages > 2 && stages * (stage_bytes + 16) + fixed > kGemvMaxSmem + 4096) --stages;
+  B200_CHECK_ARG(stages * (stage_bytes + 16) + fixed <= kGemvMaxSmem + 4096,
+                 "gemv: %d activation vectors of k=%d do not fit in shared memory next to the ring", B, plan->p.k);
+  plan->p.stages = stages;
+  plan->smem = stages * (stage_bytes + 16) + fixed;
+  return B200_OK;
+}
+
 int gemv_launch(const GemvPlan& plan, cudaStream_t stream, bool pdl) {
+  if (plan.batch > 1) return gemv_batch_launch(plan, stream, pdl);
   KernelFn f = pick(plan.rpw, plan.nseg, plan.pro, plan.epi);
   if (!f) {
     set_error("gemv: no kernel instantiation (nseg=%d pro=%d epi=%d)", plan.nseg, plan.pro, plan.epi);

@@ -17,6 +17,19 @@ enum GemvPro : int { PRO_PLAIN = 0, PRO_RMSNORM = 1, PRO_TP_RMSNORM = 2 };
 enum GemvEpi : int { EPI_PLAIN = 0, EPI_RESIDUAL = 1, EPI_SILU_MUL = 2, EPI_TP_PUSH = 3 };
 
 constexpr int kMaxTpWorld = 8;
+constexpr int kMaxBatch = 8;   // sequences one batched decode step serves (gemv_batch.cu: W streamed once for all of them)
+
+// kernel geometry shared by gemv.cu and gemv_batch.cu
+namespace gemvk {
+constexpr int kNW = 8;                      // consumer warps
+constexpr int kThreads = (kNW + 1) * 32;    // + 1 producer warp
+constexpr int kBoxK = 256;                  // columns per 512-byte row piece
+constexpr int kRowBytes = kBoxK * 2;        // 512
+constexpr int kConsumers = kNW * 32;
+constexpr int kMaxStages = 32;
+// 256-column pieces per pipeline stage: every stage carries 16 KB (32 KB for RPW 4 × 2 segments)
+__host__ __device__ constexpr int kboxes(int rpw, int nseg) { return (4 / (rpw * nseg)) > 0 ? 4 / (rpw * nseg) : 1; }
+}  // namespace gemvk
 
 struct GemvParams {
   const __nv_bfloat16* x;         // [k] activation
@@ -25,6 +38,9 @@ struct GemvParams {
   const __nv_bfloat16* bias;      // [n] or null
   const __nv_bfloat16* residual;  // [n]; may alias y
   __nv_bfloat16* y;               // [n]
+  // batched decode (gemv_batch.cu): `batch` sequences, x / residual / y of sequence b at b·stride elements
+  int batch;                      // 0 or 1: the single-sequence kernels
+  int x_stride, y_stride;         // = k, n (residual uses y_stride)
   int n;                          // output rows (per segment)
   int k;                          // reduction length
   int k_pad;                      // k rounded up to the 256-element TMA box
@@ -54,6 +70,7 @@ struct GemvPlan {
   int epi;
   int grid;
   int smem;
+  int batch;   // > 1: gemv_batch_kernel with MB = 2 / 4 / 8 (gemv_plan_set_batch)
 };
 
 // Plan a GEMV over W[rows_total, k] (row-major bf16).  `n` = rows produced (per segment).
@@ -66,6 +83,11 @@ int gemv_make_plan(GemvPlan* plan, const void* W, int64_t rows_total, int64_t n,
                    int num_sms, int smem_budget = kGemvDefaultSmem);
 int gemv_smem_wanted(int64_t n, int64_t k, int nseg, int num_sms);
 int gemv_launch(const GemvPlan& plan, cudaStream_t stream, bool pdl);
+// Turn a single-sequence plan into a batched one: B ≤ kMaxBatch activation vectors staged side by side (B · k_pad bf16 of
+// shared memory taken from the ring), x / y / residual strides set to k / n.  Single-GPU prologues / epilogues only.
+int gemv_plan_set_batch(GemvPlan* plan, int B);
+int gemv_batch_launch(const GemvPlan& plan, cudaStream_t stream, bool pdl);   // gemv_batch.cu
+int gemv_batch_setup_attributes();
 int gemv_setup_attributes();  // cudaFuncSetAttribute(max dynamic smem) for every instantiation, once per process
 
 }  // namespace b200

@@ -217,6 +217,13 @@ __global__ void __launch_bounds__(256) argmax_kernel(int64_t* __restrict__ out, 
         asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(c), "r"(__float_as_uint(v)), "r"(tag) : "memory");
         asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(c + 1), "r"(gidx), "r"(tag) : "memory");
       }
+    } else if (pub.cur_tok != nullptr && pub.batch_rows > 1) {
+      // batched engine: every row (sequence) publishes its own token; row 0 advances the shared position
+      pub.cur_tok[row] = idx;
+      const unsigned long long c = pub.gen_count[row];
+      pub.gen_log[(c % (unsigned long long)pub.gen_cap) * (unsigned long long)pub.batch_rows + row] = idx;
+      pub.gen_count[row] = c + 1;
+      if (row == 0 && pub.pos != nullptr) *pub.pos += 1;
     } else if (pub.cur_tok != nullptr && row == 0) {
       // engine: the greedy token becomes the next step's input and is appended to the on-device log
       *pub.cur_tok = idx;

@@ -16,11 +16,14 @@ int argmax_chunks(int64_t V);
 int64_t argmax_workspace_bytes(int64_t rows, int64_t V);
 // Optional tail of the engine's argmax: the last CTA publishes the greedy token as the next step's input.
 struct ArgmaxPublish {
+  // rows > 1 (batched decode): row r publishes into cur_tok[r], gen_log[r · gen_cap + …], gen_count[r]; row 0 alone
+  // advances the (shared) position and posts to the mailbox
   int* pos = nullptr;  // position counter advanced for the next token
   int64_t* cur_tok = nullptr;
   int64_t* gen_log = nullptr;
   unsigned long long* gen_count = nullptr;
   int gen_cap = 1;
+  int batch_rows = 0;   // > 1: per-row publication (see above); the log is [gen_cap][batch_rows]
   // tensor parallel (vocabulary-sharded lm_head): instead of publishing, push (max logit, GLOBAL index) into every
   // rank's candidate slot and bump its arrival counter; tp_finish_kernel (engine.cu) picks the winner.
   // async token pipeline: ring in pinned, device-mapped host memory (b200_engine_set_mailbox); null = none
@@ -78,6 +81,11 @@ struct AttnDecodeParams {
   int heads_per_cta;             // 0 = choose from max_ctx (attn_heads_per_cta)
   unsigned long long* trace;     // debug timestamps (see GemvParams::trace)
   int Hq, Hkv, nsplit, max_ctx;  // nsplit = attn_decode_nsplit(hd, max_ctx): fixed 256 (hd 64) / 128 (hd 128) keys per split
+  // batched decode: grid.z = batch sequences at the SAME position (the reference's left-padded batch,
+  // src/engine/GPTEngine.cpp:101-144); sequence b's buffers are b·stride elements further on
+  int batch;                     // 0 / 1: one sequence
+  long long qkv_bstride, out_bstride, cache_bstride, ws_bstride;
+  int tick_bstride;
 };
 int attn_decode_nsplit(int hd, int max_ctx);
 int attn_heads_per_cta(int Hq, int Hkv, int max_ctx);

@@ -3,7 +3,7 @@
 // b200_engine_set_sampler, the last kernels of a token when any sampler knob is set.  On hardware: drawn index equal to
 // the pinned sampler oracle over 10 configurations × 5 uniform numbers × 4 vocabularies, deterministic, and every token
 // an engine draws replayable on the host (tests/test_async_sampler_gpu.py).
-// Parity target: the reference's Sampler arithmetic in fp32 (its CPU path, oracle/sampler_oracle.py pinned against the
+// Parity target: the reference's Sampler arithmetic in fp32 (its CPU path; the test-side sampler oracle is pinned against the
 // reference's own Sampler.cpp).  The reference's CUDA path runs the same pipeline in the logits' dtype (bf16 divide,
 // softmax and cumsum, src/engine/Sampler.cpp:36-55) and leaves equal logits at a cut to thrust's unstable sort: a
 // top-p / min-p boundary can differ by an entry from it.  The uniform number is Philox(seed, tokens this ENGINE has

@@ -128,31 +128,50 @@ class DecodeEngine:
     def forward(self, ids: torch.Tensor, all_positions: bool = False) -> torch.Tensor:
         """ids [1, S] int64 on the device → logits [1, S, V] (all_positions) or [1, 1, V] (last position) bf16.
         (Tensor-parallel engines return this rank's vocabulary shard, V / world columns.)"""
-        if ids.dim() != 2 or ids.shape[0] != 1:
-            raise B200Error("DecodeEngine.forward: ids must be [1, S] (batch-1 engine)")
+        if ids.dim() != 2 or not 1 <= ids.shape[0] <= 8:
+            raise B200Error("DecodeEngine.forward: ids must be [B, S] with 1 ≤ B ≤ 8 (sequences at the same position)")
         if ids.dtype != torch.int64 or not ids.is_cuda:
             raise B200Error("DecodeEngine.forward: ids must be int64 on the device (reference: FuncNNLayer.h:205)")
         ids = ids.contiguous()
-        S = ids.shape[1]
+        B, S = ids.shape
         rows = S if all_positions else 1
-        logits = torch.empty(1, rows, self.local_vocab, dtype=torch.bfloat16, device=self.device)
-        check(lib().b200_engine_forward(self._h, ids.data_ptr(), 1, S, logits.data_ptr(), int(all_positions),
+        logits = torch.empty(B, rows, self.local_vocab, dtype=torch.bfloat16, device=self.device)
+        check(lib().b200_engine_forward(self._h, ids.data_ptr(), B, S, logits.data_ptr(), int(all_positions),
                                         self._stream()), "b200_engine_forward")
+        self._batch = B
         return logits
 
     def gen_next_token(self, ids: torch.Tensor) -> torch.Tensor:
-        """genNextToken: forward → last position → greedy argmax (device tensor [1, 1] int64)."""
-        check(lib().b200_engine_forward(self._h, ids.contiguous().data_ptr(), 1, ids.shape[1], None, 0, self._stream()),
+        """genNextToken: forward → last position → greedy argmax (device tensor [B, 1] int64)."""
+        B = ids.shape[0]
+        check(lib().b200_engine_forward(self._h, ids.contiguous().data_ptr(), B, ids.shape[1], None, 0, self._stream()),
               "b200_engine_forward")
-        out = torch.empty(1, 1, dtype=torch.int64, device=self.device)
+        self._batch = B
+        out = torch.empty(B, 1, dtype=torch.int64, device=self.device)
         check(lib().b200_engine_last_token(self._h, out.data_ptr(), self._stream()), "b200_engine_last_token")
         return out
 
     def decode(self, n_steps: int) -> torch.Tensor:
-        """n greedy steps on the device, each consuming the previous step's token → int64 [n] device tensor."""
-        out = torch.empty(n_steps, dtype=torch.int64, device=self.device)
+        """n greedy steps on the device, each consuming the previous step's token → int64 [n] device tensor (after a
+        batched forward with B > 1 sequences: [n, B])."""
+        B = getattr(self, "_batch", 1)
+        out = torch.empty((n_steps, B) if B > 1 else (n_steps,), dtype=torch.int64, device=self.device)
         check(lib().b200_engine_decode(self._h, n_steps, out.data_ptr(), self._stream()), "b200_engine_decode")
         return out
+
+    def generate_sync_batch(self, prompts: torch.Tensor, max_new_tokens: int) -> torch.Tensor:
+        """GPTEngine::generateSync for a batch of equally long (left-padded) prompts [B, S] with HOST buffers
+        [ref: src/engine/GPTEngine.cpp:154-174]: one weight pass per step for the whole batch.  → CPU int64 [B, new]."""
+        prompts = torch.as_tensor(prompts, dtype=torch.int64)
+        if prompts.dim() != 2 or prompts.shape[0] < 1:
+            raise B200Error("generate_sync_batch: prompts must be [B, S]")
+        ids = prompts.pin_memory().to(self.device, non_blocking=True)
+        self.reset_cache()
+        first = self.gen_next_token(ids)                       # [B, 1]
+        rest = self.decode(max_new_tokens - 1)                 # [n-1, B] (or [n-1] for B = 1)
+        rest = rest.view(max_new_tokens - 1, -1).t()
+        toks = torch.cat([first, rest], dim=1).cpu()
+        return toks
 
     # ------------------------------------------------------------------------------------------ generateSync
     def generate_sync(self, prompt_ids: List[int] | torch.Tensor, max_new_tokens: int,

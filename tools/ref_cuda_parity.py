@@ -36,7 +36,7 @@ FAMILY = {"llama": "llama", "qwen2": "qwen2", "qwen3": "qwen3", "mistral": "mist
 
 
 def run_reference(spec, ckpt_dir, prompt, n_new, forced=None, time_steps=0, timeout=1200, b200="off", batched=False,
-                  dump_rope=None):
+                  dump_rope=None, batch=1):
     """→ (tokens [n_new] int64, logits [n_new, V] float32, timing dict or None) from the reference CUDA binary.
     b200 = "ops" / "engine": the same reference program with our kernels behind its op registry (boundary B) / our
     engine behind GPTModel::model() (boundary A), through integration/tinytorch_b200_adapter.h."""
@@ -60,12 +60,18 @@ def run_reference(spec, ckpt_dir, prompt, n_new, forced=None, time_steps=0, time
         cmd += ["--batched", "1"]
     if dump_rope:
         cmd += ["--dump-rope", str(dump_rope)]
+    if batch > 1:   # prompt: [B][S] ids, forced: [N][B]; returns tokens [N, B], logits [N, B, V]
+        cmd += ["--batch", str(batch)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
     if r.returncode != 0:
         raise RuntimeError(f"ref_cuda_decode failed ({r.returncode}): {r.stderr[-800:]}")
     raw = (d / "ref_out.bin").read_bytes()
-    toks = np.frombuffer(raw[: 8 * n_new], dtype=np.int64).copy()
-    logits = np.frombuffer(raw[8 * n_new:], dtype=np.float32).reshape(n_new, spec.vocab).copy()
+    toks = np.frombuffer(raw[: 8 * n_new * batch], dtype=np.int64).copy()
+    logits = np.frombuffer(raw[8 * n_new * batch:], dtype=np.float32).copy()
+    if batch > 1:
+        toks, logits = toks.reshape(n_new, batch), logits.reshape(n_new, batch, spec.vocab)
+    else:
+        logits = logits.reshape(n_new, spec.vocab)
     timing = None
     for line in r.stdout.splitlines():
         if line.startswith("{"):
