@@ -566,6 +566,19 @@ def run_ours(args):
         ref = CpuReference(args.model)
         v, sample = ref.step(8)
         cpu = {"value": v, "unit": "tokens/s", "cores": ref.cores, "kind": ref.kind, "sample": sample}
+        # BASELINE config 1 — GPT-2 124M fp32 `--device cpu`, 32 new tokens: the one family whose forward exists on the
+        # reference's CPU path unmodified (examples/inference/main.cpp:39-62); reported once, beside the headline's arm
+        if ref.kind == "reference":
+            try:
+                out = subprocess.run([str(ref.ref_bin), "--model", "GPT-2-124M", "--prompt", "7", "--tokens", "32", "--fp32", "1"],
+                                     capture_output=True, text=True, timeout=240)
+                for ln in out.stdout.splitlines():
+                    if ln.startswith("{"):
+                        g = json.loads(ln)
+                        cpu["config1_gpt2_124m_fp32_cpu"] = {"value": g["tokens_per_s"], "unit": "tokens/s", "cores": 1,
+                                                              "sample": g.get("sample", "")}
+            except Exception as e:  # noqa: BLE001
+                cpu["config1_gpt2_124m_fp32_cpu"] = {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
 
     # ---- the reference's OWN CUDA path on this GPU (rank 0, N = 1 only), run as a separate process AFTER every
     # measurement of ours: the meaningful speed anchor (cpu_baseline is one core of naive loops)

@@ -42,6 +42,7 @@ int main(int argc, char** argv) {
   else if (model == "Llama-3.2-3B") d = {0, 3072, 28, 24, 8, 128, 8192, 128256, 256, 5e5f, 1e-5f, 1, 32.f, 4.f, 1.f, 8192, 1};
   else if (model == "Qwen3-1.7B") d = {2, 2048, 28, 16, 8, 128, 6144, 151936, 256, 1e6f, 1e-6f, 1, 0, 0, 0, 0, 1};
   else if (model == "Mistral-7B-v0.3") d = {3, 4096, 32, 32, 8, 128, 14336, 32768, 256, 1e6f, 1e-5f, 0, 0, 0, 0, 0, 1};
+  else if (model == "GPT-2-124M") d = {4, 768, 12, 12, 12, 64, 3072, 50257, 1024, 0.f, 1e-5f, 1, 0, 0, 0, 0, 0};   // fp32
   else { fprintf(stderr, "unknown model %s\n", model.c_str()); return 2; }
   if (fp32) d.bf16 = 0;
   void* m = ref_model_create(&d);
@@ -59,7 +60,9 @@ int main(int argc, char** argv) {
     for (int64_t j = 0; j < cnt; j++) {
       s = s * 6364136223846793005ull + 1442695040888963407ull;
       const float u = (float)((s >> 40) & 0xFFFFFF) / 16777216.0f;  // [0,1)
-      buf[j] = (is_norm ? 1.0f : 0.0f) + (u - 0.5f) * 0.07f;
+      const bool is_ln_bias = strstr(name, "ln_") != nullptr && strstr(name, "bias") != nullptr;   // GPT-2 LayerNorm β
+      const bool is_ln_gain = (is_norm || strstr(name, "ln_") != nullptr) && !is_ln_bias;
+      buf[j] = (is_ln_gain ? 1.0f : 0.0f) + (is_ln_bias ? 0.f : (u - 0.5f) * 0.07f);
     }
     ref_model_set_state(m, i, buf.data());
   }
@@ -81,8 +84,9 @@ int main(int argc, char** argv) {
   const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   printf("{\"tokens_per_s\": %.6f, \"threads\": 1, \"seconds\": %.3f, \"sample\": \"%d greedy decode steps after a "
          "%d-token prompt, %s %s on the reference's own CPU ops (single-threaded naive GEMM, "
-         "third_party/TinyTorch/src/Operation/OpLinalgCpu.h:119-151) + naive attention shim\"}\n",
-         tokens / dt, dt, tokens, prompt, model.c_str(), d.bf16 ? "bf16" : "fp32");
+         "third_party/TinyTorch/src/Operation/OpLinalgCpu.h:119-151)%s\"}\n",
+         tokens / dt, dt, tokens, prompt, model.c_str(), d.bf16 ? "bf16" : "fp32",
+         d.family == 4 ? ", unmodified (sdpAttention)" : " + naive attention shim");
   fflush(stdout);
   _exit(0);  // skip static destructors: the reference's allocator asserts on teardown order
 }

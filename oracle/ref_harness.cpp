@@ -17,6 +17,7 @@
 
 #include "Functions.h"
 #include "Modules.h"
+#include "model/ModelGPT2.h"
 #include "model/ModelLlama.h"
 #include "model/ModelMistral.h"
 #include "model/ModelQwen2.h"
@@ -188,7 +189,7 @@ int64_t ref_sampler_f32(const float* logits, int64_t V, float temperature, int64
 
 // ---- whole model ---------------------------------------------------------------------------------------------
 struct RefModelDesc {
-  int32_t family;  // 0 llama, 1 qwen2, 2 qwen3, 3 mistral
+  int32_t family;  // 0 llama, 1 qwen2, 2 qwen3, 3 mistral, 4 gpt2 (hidden = n_embd, q_heads = n_head, max_ctx = n_positions)
   int32_t hidden, layers, q_heads, kv_heads, head_dim, intermediate, vocab, max_ctx;
   float rope_theta, rms_eps;
   int32_t tie;
@@ -201,6 +202,7 @@ struct RefModel {
   tinygpt::huggingface::model::LlamaConfig llama;
   tinygpt::huggingface::model::QwenConfig qwen;
   tinygpt::huggingface::model::MistralConfig mistral;
+  tinygpt::huggingface::model::GPT2Config gpt2;
   std::unique_ptr<tinygpt::GPTModel> model;
 };
 
@@ -244,6 +246,17 @@ void* ref_model_create(const RefModelDesc* d) {
         m->model = std::make_unique<tinygpt::ModelQwen2>(m->qwen, cpu);
       else
         m->model = std::make_unique<tinygpt::ModelQwen3>(m->qwen, cpu);
+      break;
+    case 4:   // BASELINE config 1: GPT-2, the only family whose forward exists on the reference's CPU path unmodified
+      fillCommon(m->gpt2, *d);
+      m->gpt2.activationFunction = "gelu_new";
+      m->gpt2.layerNormEpsilon = d->rms_eps;
+      m->gpt2.nCtx = d->max_ctx;
+      m->gpt2.nEmbd = d->hidden;
+      m->gpt2.nHead = d->q_heads;
+      m->gpt2.nLayer = d->layers;
+      m->gpt2.nPositions = d->max_ctx;
+      m->model = std::make_unique<tinygpt::ModelGPT2>(m->gpt2, cpu);
       break;
     default:
       fillCommon(m->mistral, *d);
