@@ -259,7 +259,8 @@ int64_t b200_engine_generated(const b200_engine* eng);
  * Returns the number of launches copied (0 when tracing is off). */
 int64_t b200_engine_debug_trace(b200_engine* eng, uint64_t* out_host, int64_t max_entries);
 
-/* Host-side mirrors (no device access): tokens consumed so far, and kernels per decoded token. */
+/* Host-side mirrors (no device access): tokens consumed so far, and kernels per decoded token (of the batched graph
+ * while the engine holds a batch: the same nodes, plus one per layer when the down projection runs in two groups). */
 int64_t b200_engine_position(const b200_engine* eng);
 int64_t b200_engine_launches_per_token(const b200_engine* eng);
 /* Which code paths this engine was built with (environment / defaults at create time): bit 0 CUDA graph, bit 1

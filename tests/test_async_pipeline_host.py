@@ -155,3 +155,18 @@ def test_philox_known_answers():
     assert c == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
     us = [engine.DecodeEngine.philox_uniform(7, n) for n in range(2000)]
     assert all(0.0 < u < 1.0 for u in us) and 0.45 < sum(us) / len(us) < 0.55 and len(set(us)) > 1990
+
+
+# ---------------------------------------------------------------------------------------------- ragged batches (host)
+def test_align_prompts_follows_encode_texts():
+    """GPTEngine::encodeTexts [ref: src/engine/GPTEngine.cpp:101-141]: common length = min(longest, context), longer
+    prompts keep their last tokens, shorter ones are padded on the left; the mask marks the real tokens."""
+    ids, mask = engine.align_prompts([[5, 6, 7], [1], [2, 3, 4, 8, 9]], context_size=64, pad_token=42)
+    assert ids.tolist() == [[42, 42, 5, 6, 7], [42, 42, 42, 42, 1], [2, 3, 4, 8, 9]]
+    assert mask.tolist() == [[False, False, True, True, True], [False] * 4 + [True], [True] * 5]
+    ids, mask = engine.align_prompts([[1, 2, 3, 4, 5, 6], [7, 8]], context_size=4, pad_token=0)       # truncation
+    assert ids.tolist() == [[3, 4, 5, 6], [0, 0, 7, 8]] and mask.tolist() == [[True] * 4, [False, False, True, True]]
+    ids, mask = engine.align_prompts([[9, 9]], context_size=8, pad_token=0)                           # batch of one
+    assert ids.tolist() == [[9, 9]] and bool(mask.all())
+    with pytest.raises(B200Error):
+        engine.align_prompts([], 8, 0)

@@ -63,6 +63,35 @@ def test_batched_decode_is_bitwise_the_batch1_engine(built_lib, spec, B, S):
     # host-buffer API
     eng2 = eng.generate_sync_batch(prompts, n_new)
     assert torch.equal(eng2, want_toks.t())
+    # ragged prompts are aligned the reference's way (left padding; the pads are attended, GPTEngine.cpp:95) — the same
+    # batch as the padded ids given directly
+    ragged = [prompts[b, min(b, S - 1):].tolist() for b in range(B)]
+    padded, _ = engine.align_prompts(ragged, spec.max_ctx, 7)
+    assert torch.equal(eng.generate_sync_batch(ragged, 4, pad_token=7), eng.generate_sync_batch(padded, 4))
+    eng.close()
+
+
+@pytest.mark.parametrize("B", [5, 8])
+def test_batched_decode_wide_ffn_splits_the_down_projection(built_lib, B):
+    """Mistral-7B's FFN width (k = 14336 for the down projection): 8 activation vectors of that length do not fit next
+    to a useful ring, so the batched GEMV runs as launches of 4 sequences (csrc/gemv.cu gemv_plan_set_batch, `sub`) — same
+    per-sequence arithmetic, so still bit-identical to batch-1 runs, uneven last group (B = 5) included."""
+    spec = models.ModelSpec("tiny-wide-ffn", "mistral", 256, 2, 4, 2, 64, 14336, 512, 1e6, 1e-5, tie=False, max_ctx=64)
+    w = {k: v.to(DEV) for k, v in models.synth_weights(spec, seed=9).items()}
+    prompts = torch.randint(0, spec.vocab, (B, 6), generator=torch.Generator().manual_seed(B))
+    n_new = 6
+    want_logits, want_toks = _single_runs(spec, w, prompts, n_new)
+    eng = engine.DecodeEngine(spec, w)
+    eng.reset_cache()
+    first = eng.gen_next_token(prompts.to(DEV))
+    toks = torch.cat([first.view(1, B), eng.decode(n_new - 1).view(n_new - 1, B)]).cpu()
+    assert torch.equal(toks, want_toks)
+    eng.reset_cache()
+    logits = [eng.forward(prompts.to(DEV))[:, -1].float().cpu()]
+    for i in range(n_new - 1):
+        logits.append(eng.forward(toks[i].view(B, 1).to(DEV))[:, -1].float().cpu())
+    assert torch.equal(torch.stack(logits), want_logits)
+    assert eng.launches_per_token > 1 + 5 * spec.layers + 2 - 1      # the extra down-projection launches are counted
     eng.close()
 
 

@@ -1109,7 +1109,10 @@ int64_t b200_engine_debug_trace(b200_engine* e, uint64_t* out_host, int64_t max_
   if (cudaMemcpy(out_host, e->trace, (size_t)n * 8 * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
   return n;
 }
-int64_t b200_engine_launches_per_token(const b200_engine* e) { return e ? e->launches_per_token : -1; }
+int64_t b200_engine_launches_per_token(const b200_engine* e) {
+  if (!e) return -1;
+  return e->batch > 1 && e->b_cap == e->batch ? e->b_launches : e->launches_per_token;   // the graph the next step runs
+}
 int64_t b200_engine_options(const b200_engine* e) {
   if (!e) return -1;
   return (e->use_graph ? 1 : 0) | (e->use_pdl ? 2 : 0) | (e->use_prefill_gemm ? 8 : 0);

@@ -525,15 +525,25 @@ int gemv_plan_set_batch(GemvPlan* plan, int B) {
   plan->p.batch = B;
   plan->p.x_stride = plan->p.k;
   plan->p.y_stride = plan->p.n;
+  plan->sub = 0;
   if (B == 1) return B200_OK;
-  const int mb = B <= 2 ? 2 : B <= 4 ? 4 : 8;
   const int kb = kboxes(plan->rpw, plan->nseg);
   const int stage_bytes = kb * plan->nseg * 8 * plan->rpw * kRowBytes;
-  const int fixed = mb * plan->p.k_pad * 2 + 64 + mb * kNW * 4;
-  int stages = plan->p.stages;
-  while (stages > 2 && stages * (stage_bytes + 16) + fixed > kGemvMaxSmem + 4096) --stages;
-  B200_CHECK_ARG(stages * (stage_bytes + 16) + fixed <= kGemvMaxSmem + 4096,
-                 "gemv: %d activation vectors of k=%d do not fit in shared memory next to the ring", B, plan->p.k);
+  // MB activation vectors are staged next to the ring.  When they leave fewer than 4 stages (only the down projection
+  // of the widest FFN: k = 14336, B > 4), halve the sequences per launch instead and stream W once per half — a
+  // 2-stage ring costs more than the second weight pass.
+  int mb = B <= 2 ? 2 : B <= 4 ? 4 : 8;
+  int stages = 0, fixed = 0;
+  for (;; mb >>= 1) {
+    fixed = mb * plan->p.k_pad * 2 + 64 + mb * kNW * 4;
+    stages = plan->p.stages;
+    while (stages > 2 && stages * (stage_bytes + 16) + fixed > kGemvMaxSmem + 4096) --stages;
+    const bool fits = stages * (stage_bytes + 16) + fixed <= kGemvMaxSmem + 4096;
+    if (fits && (stages >= 4 || stages == plan->p.stages || mb == 2)) break;
+    B200_CHECK_ARG(mb > 2, "gemv: %d activation vectors of k=%d do not fit in shared memory next to the ring", B,
+                   plan->p.k);
+  }
+  if (mb < B) plan->sub = mb;
   plan->p.stages = stages;
   plan->smem = stages * (stage_bytes + 16) + fixed;
   return B200_OK;

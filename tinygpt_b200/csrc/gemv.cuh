@@ -71,6 +71,8 @@ struct GemvPlan {
   int grid;
   int smem;
   int batch;   // > 1: gemv_batch_kernel with MB = 2 / 4 / 8 (gemv_plan_set_batch)
+  int sub;     // sequences per launch when `batch` activation vectors do not fit beside the ring (k = 14336 at B = 8:
+               // two launches of 4, W streamed twice); 0 = all of them in one launch
 };
 
 // Plan a GEMV over W[rows_total, k] (row-major bf16).  `n` = rows produced (per segment).

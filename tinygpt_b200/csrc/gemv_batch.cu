@@ -296,14 +296,25 @@ int gemv_batch_setup_attributes() {
 }
 
 int gemv_batch_launch(const GemvPlan& plan, cudaStream_t stream, bool pdl) {
-  const int mb = plan.batch <= 2 ? 2 : plan.batch <= 4 ? 4 : 8;
+  const int per = plan.sub > 0 ? plan.sub : plan.batch;   // sequences per launch (gemv_plan_set_batch)
+  const int mb = per <= 2 ? 2 : per <= 4 ? 4 : 8;
   KernelFn f = pick(plan.rpw, plan.nseg, plan.pro, plan.epi, mb);
   if (!f) {
     set_error("batched gemv: no kernel instantiation (rpw=%d nseg=%d pro=%d epi=%d batch=%d)", plan.rpw, plan.nseg, plan.pro,
               plan.epi, plan.batch);
     return B200_ERR_INVALID;
   }
-  B200_CUDA(launch_pdl(f, dim3(plan.grid), dim3(kThreads), (size_t)plan.smem, stream, pdl, plan.p, plan.tmap));
+  for (int b0 = 0; b0 < plan.batch; b0 += per) {
+    GemvParams p = plan.p;
+    p.batch = plan.batch - b0 < per ? plan.batch - b0 : per;
+    p.x += (size_t)b0 * p.x_stride;
+    p.y += (size_t)b0 * p.y_stride;
+    if (p.residual) p.residual += (size_t)b0 * p.y_stride;
+    const bool last = b0 + per >= plan.batch;
+    if (!last) p.pos_inc = nullptr;                       // the position advances once, after the last launch
+    // every launch waits on its predecessor (griddepcontrol.wait), so the chain stays ordered through the halves
+    B200_CUDA(launch_pdl(f, dim3(plan.grid), dim3(kThreads), (size_t)plan.smem, stream, pdl, p, plan.tmap));
+  }
   return B200_OK;
 }
 

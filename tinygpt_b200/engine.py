@@ -20,6 +20,24 @@ from . import models
 from ._lib import B200Error, LayerWeights, ModelDesc, WeightTable, check, lib, require_device
 
 
+def align_prompts(token_lists, context_size: int, pad_token: int):
+    """GPTEngine::encodeTexts' alignment of a ragged batch [ref: src/engine/GPTEngine.cpp:101-141]: the common length is
+    min(longest prompt, context size); longer prompts keep their LAST tokens, shorter ones are padded on the LEFT with
+    `pad_token` (the tokenizer's pad id, else eos, else 0 — the caller resolves that).  → (ids int64 [B, S], mask bool
+    [B, S] with False on the pads; the reference builds the mask and then ignores it, and so does the engine)."""
+    if len(token_lists) == 0:
+        raise B200Error("align_prompts: empty batch")
+    S = min(max(len(t) for t in token_lists), int(context_size))
+    ids = torch.full((len(token_lists), S), int(pad_token), dtype=torch.int64)
+    mask = torch.zeros((len(token_lists), S), dtype=torch.bool)
+    for i, t in enumerate(token_lists):
+        t = list(t)[-S:] if S > 0 else []
+        if t:
+            ids[i, S - len(t):] = torch.tensor(t, dtype=torch.int64)
+            mask[i, S - len(t):] = True
+    return ids, mask
+
+
 class DecodeEngine:
     """Whole-token engine for ONE sequence (batch 1) on the current CUDA device.
 
@@ -159,9 +177,14 @@ class DecodeEngine:
         check(lib().b200_engine_decode(self._h, n_steps, out.data_ptr(), self._stream()), "b200_engine_decode")
         return out
 
-    def generate_sync_batch(self, prompts: torch.Tensor, max_new_tokens: int) -> torch.Tensor:
-        """GPTEngine::generateSync for a batch of equally long (left-padded) prompts [B, S] with HOST buffers
-        [ref: src/engine/GPTEngine.cpp:154-174]: one weight pass per step for the whole batch.  → CPU int64 [B, new]."""
+    def generate_sync_batch(self, prompts, max_new_tokens: int, pad_token: int = 0) -> torch.Tensor:
+        """GPTEngine::generateSync for a batch of prompts with HOST buffers [ref: src/engine/GPTEngine.cpp:154-174]: one
+        weight pass per step for the whole batch.  `prompts`: [B, S] ids, or a list of ragged id lists that is aligned
+        the reference's way first (`align_prompts`: left padding with `pad_token`, truncation to the context; like the
+        reference, the pad positions are attended — its mask is a TODO, GPTEngine.cpp:95).  → CPU int64 [B, new]."""
+        if isinstance(prompts, (list, tuple)) and len(prompts) and not torch.is_tensor(prompts[0]) \
+                and len({len(p) for p in prompts}) > 1:
+            prompts, _ = align_prompts(prompts, self.spec.max_ctx, pad_token)
         prompts = torch.as_tensor(prompts, dtype=torch.int64)
         if prompts.dim() != 2 or prompts.shape[0] < 1:
             raise B200Error("generate_sync_batch: prompts must be [B, S]")
