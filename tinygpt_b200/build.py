@@ -29,6 +29,7 @@ NVCC_FLAGS = [
     "--expt-relaxed-constexpr",
     "-Xcompiler", "-fPIC,-fno-exceptions,-fvisibility=hidden",
     "-Xptxas", "-v",
+    *os.environ.get("B200_NVCC_EXTRA", "").split(),   # e.g. -DB200_DIAG_PROLOGUE (diagnostic stamps, tools/trace_decode.py)
 ]
 
 

@@ -336,9 +336,14 @@ static int engine_launch_token_batch(b200_engine* e, cudaStream_t st, bool with_
                        (int64_t)d.vocab, (int)d.hidden));
   const size_t kv_layer = (size_t)d.max_ctx * e->Hkv_l * d.head_dim;
   const int nqkv = e->qdim + 2 * e->kvdim;
+  int slot = 0;
+  auto tr = [&]() -> unsigned long long* { return e->trace ? e->trace + 8 * (slot++) : nullptr; };
   for (int l = 0; l < d.layers; ++l) {
-    if ((rc = gemv_launch(e->bp_qkv[l], st, pdl)) != B200_OK) return rc;
+    GemvPlan q = e->bp_qkv[l];
+    q.p.trace = tr();
+    if ((rc = gemv_launch(q, st, pdl)) != B200_OK) return rc;
     AttnDecodeParams a{};
+    a.trace = tr();
     a.qkv = e->bqkv;
     a.q_norm = (const __nv_bfloat16*)e->lw[l].q_norm;
     a.k_norm = (const __nv_bfloat16*)e->lw[l].k_norm;
@@ -361,15 +366,21 @@ static int engine_launch_token_batch(b200_engine* e, cudaStream_t st, bool with_
     a.ws_bstride = attn_decode_ws_floats(e->Hq_l, e->Hkv_l, d.head_dim, e->nsplit);
     a.tick_bstride = e->Hq_l;
     if ((rc = launch_attn_decode(a, d.head_dim, st, pdl)) != B200_OK) return rc;
-    if ((rc = gemv_launch(e->bp_o[l], st, pdl)) != B200_OK) return rc;
-    if ((rc = gemv_launch(e->bp_gu[l], st, pdl)) != B200_OK) return rc;
+    GemvPlan o = e->bp_o[l], gu = e->bp_gu[l];
+    o.p.trace = tr();
+    gu.p.trace = tr();
+    if ((rc = gemv_launch(o, st, pdl)) != B200_OK) return rc;
+    if ((rc = gemv_launch(gu, st, pdl)) != B200_OK) return rc;
     const bool last_node = !with_head && l == d.layers - 1;
     GemvPlan dn = e->bp_down[l];
     dn.p.pos_inc = last_node ? e->pos : nullptr;   // the LAST kernel of a token advances the position
+    dn.p.trace = tr();
     if ((rc = gemv_launch(dn, st, pdl && !last_node)) != B200_OK) return rc;
   }
   if (with_head) {
-    if ((rc = gemv_launch(e->bp_head, st, pdl)) != B200_OK) return rc;
+    GemvPlan hd = e->bp_head;
+    hd.p.trace = tr();
+    if ((rc = gemv_launch(hd, st, pdl)) != B200_OK) return rc;
     int64_t* amax = reinterpret_cast<int64_t*>((uint8_t*)e->b_argmax_ws + argmax_workspace_bytes(B, e->V_l));
     ArgmaxPublish pub;
     pub.pos = e->pos;

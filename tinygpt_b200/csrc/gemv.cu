@@ -77,6 +77,7 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
     // ------------------------------------------------------------------ producer: one thread drives the TMA ring
     if (lane == 0) {
       tma_prefetch_desc(&tmap);
+      const uint64_t pol = l2_policy_evict_first();   // every weight byte is read once per token
       int s = 0;
       uint32_t ph = 1;  // first pass over the ring: slots are free (wait on the "previous" phase returns at once)
       for (int i = 0; i < my_rbs; ++i) {
@@ -89,7 +90,7 @@ gemv_stream_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap)
           // describes W in 2/4/8-byte elements so that the inner box dimension stays ≤ 256, gemv_make_plan)
 #pragma unroll
           for (int seg = 0; seg < NSEG; ++seg)
-            tma_load_2d(dst + seg * (KB * kBoxBytes), &tmap, ks * kBoxK, seg * p.seg_rows + row0, &full[s]);
+            tma_load_2d_hint(dst + seg * (KB * kBoxBytes), &tmap, ks * kBoxK, seg * p.seg_rows + row0, &full[s], pol);
           if (++s == p.stages) {
             s = 0;
             ph ^= 1;
@@ -529,13 +530,13 @@ int gemv_plan_set_batch(GemvPlan* plan, int B) {
   if (B == 1) return B200_OK;
   const int kb = kboxes(plan->rpw, plan->nseg);
   const int stage_bytes = kb * plan->nseg * 8 * plan->rpw * kRowBytes;
-  // MB activation vectors are staged next to the ring.  When they leave fewer than 4 stages (only the down projection
+  // The activation vectors are staged next to the ring.  When they leave fewer than 4 stages (only the down projection
   // of the widest FFN: k = 14336, B > 4), halve the sequences per launch instead and stream W once per half — a
   // 2-stage ring costs more than the second weight pass.
-  int mb = B <= 2 ? 2 : B <= 4 ? 4 : 8;
+  int mb = B;
   int stages = 0, fixed = 0;
-  for (;; mb >>= 1) {
-    fixed = mb * plan->p.k_pad * 2 + 64 + mb * kNW * 4;
+  for (;; mb = (mb + 1) >> 1) {
+    fixed = gemv_batch_fixed_smem(*plan, mb);
     stages = plan->p.stages;
     while (stages > 2 && stages * (stage_bytes + 16) + fixed > kGemvMaxSmem + 4096) --stages;
     const bool fits = stages * (stage_bytes + 16) + fixed <= kGemvMaxSmem + 4096;

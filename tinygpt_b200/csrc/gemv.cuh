@@ -70,7 +70,7 @@ struct GemvPlan {
   int epi;
   int grid;
   int smem;
-  int batch;   // > 1: gemv_batch_kernel with MB = 2 / 4 / 8 (gemv_plan_set_batch)
+  int batch;   // > 1: gemv_batch_kernel (tensor cores, gemv_batch.cu; gemv_plan_set_batch)
   int sub;     // sequences per launch when `batch` activation vectors do not fit beside the ring (k = 14336 at B = 8:
                // two launches of 4, W streamed twice); 0 = all of them in one launch
 };
@@ -90,6 +90,7 @@ int gemv_launch(const GemvPlan& plan, cudaStream_t stream, bool pdl);
 int gemv_plan_set_batch(GemvPlan* plan, int B);
 int gemv_batch_launch(const GemvPlan& plan, cudaStream_t stream, bool pdl);   // gemv_batch.cu
 int gemv_batch_setup_attributes();
+int gemv_batch_fixed_smem(const GemvPlan& plan, int nb);   // shared memory beside the ring for nb sequences
 int gemv_setup_attributes();  // cudaFuncSetAttribute(max dynamic smem) for every instantiation, once per process
 
 }  // namespace b200

@@ -11,10 +11,11 @@ from tinygpt_b200 import engine, models  # noqa: E402
 from tinygpt_b200._lib import lib  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "Qwen2.5-0.5B"
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 1          # > 1: the batched token (csrc/gemv_batch*.cu)
 spec = models.SPECS[name].with_ctx(256)
 w = {k: v.cuda() for k, v in models.synth_weights(spec, seed=0).items()}
 eng = engine.DecodeEngine(spec, w)
-prompt = torch.randint(0, spec.vocab, (1, 16), generator=torch.Generator().manual_seed(0)).cuda()
+prompt = torch.randint(0, spec.vocab, (B, 16), generator=torch.Generator().manual_seed(0)).cuda()
 eng.reset_cache()
 eng.gen_next_token(prompt)
 eng.decode(64)
@@ -33,7 +34,7 @@ for i in range(got):
     else:                                   # GEMV: slots 4-7 are SM cycles since the dependency resolved
         fine = tuple(buf[8 * i + j] / 1965.0 for j in (4, 5, 6, 7))
     rows.append((names[i % 5] if i < 5 * spec.layers else "head", i // 5, a / 1e3, b / 1e3, c / 1e3, pro, fine))
-print(f"{name}: kernel  layer  entry_us  after_wait_us  exit_us   (wait = after_wait-entry, body = exit-after_wait)")
+print(f"{name} (batch {B}): kernel  layer  entry_us  after_wait_us  exit_us   (wait = after_wait-entry, body = exit-after_wait)")
 for r in rows[:12] + rows[5 * 10:5 * 10 + 6] + rows[-6:]:
     print(f"{r[0]:5s} {r[1]:3d}  {r[2]:9.2f} {r[3]:9.2f} {r[4]:9.2f}   wait {r[3]-r[2]:6.2f}  body {r[4]-r[3]:6.2f}")
 import collections
