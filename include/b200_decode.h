@@ -220,7 +220,8 @@ int b200_engine_seek(b200_engine* eng, int64_t position, void* stream);
  *   logits_mode 0: logits_out is [B, V]      — last position only
  *   logits_mode 1: logits_out is [B, S, V]   — every position, like the reference's lm_head over all S
  * B > 1 (single-GPU, greedy engines): every sequence has its own KV cache; a decode step streams the weights ONCE for the
- * whole batch (gemv_batch.cu) and reproduces B independent batch-1 steps bit for bit.  The first call with a new B builds
+ * whole batch (gemv_batch.cu: tensor cores, the B activation vectors as the n = 8 MMA operand) and agrees with B independent
+ * batch-1 steps to summation-order noise, like the reference's own m = B GEMM against its m = 1 path.  The first call with a new B builds
  * the batch's buffers and graphs.  b200_engine_decode / b200_engine_last_token follow the batch of the latest forward.
  * After the call the engine's "current token" is the greedy argmax of the last position (reference tie rule), so
  * b200_engine_decode can continue without a host round trip.  logits_out may be NULL. */

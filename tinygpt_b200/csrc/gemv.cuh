@@ -85,8 +85,9 @@ int gemv_make_plan(GemvPlan* plan, const void* W, int64_t rows_total, int64_t n,
                    int num_sms, int smem_budget = kGemvDefaultSmem);
 int gemv_smem_wanted(int64_t n, int64_t k, int nseg, int num_sms);
 int gemv_launch(const GemvPlan& plan, cudaStream_t stream, bool pdl);
-// Turn a single-sequence plan into a batched one: B ≤ kMaxBatch activation vectors staged side by side (B · k_pad bf16 of
-// shared memory taken from the ring), x / y / residual strides set to k / n.  Single-GPU prologues / epilogues only.
+// Turn a single-sequence plan into a batched one: B ≤ kMaxBatch activation vectors staged side by side (shared memory
+// taken from the ring; `sub` < B sequences per launch when they do not fit), x / y / residual strides set to k / n.
+// Single-GPU prologues / epilogues only.
 int gemv_plan_set_batch(GemvPlan* plan, int B);
 int gemv_batch_launch(const GemvPlan& plan, cudaStream_t stream, bool pdl);   // gemv_batch.cu
 int gemv_batch_setup_attributes();

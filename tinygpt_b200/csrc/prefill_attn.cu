@@ -1,6 +1,7 @@
 // prefill_attn.cu — causal flash attention of a PREFILL chunk on the tensor cores (mma.sync m16n8k16 bf16, fp32
-// accumulate), sm_100a.  Opt-in (B200_PREFILL_ATTN=mma) until it has been run against the oracle on hardware; the
-// default prefill attention is the CUDA-core kernel in prefill.cu.
+// accumulate), sm_100a.  The default prefill attention (common.cuh Defaults::kPrefillAttnMma; parity against the oracle
+// and the reference's CUDA path: tests/test_prefill_gpu.py); B200_PREFILL_ATTN=cuda selects the CUDA-core kernel in
+// prefill.cu, which also serves the shapes this one does not tile.
 //
 // Replaces tfa::flashAttn for Sq > 1 [ref: TFA/mma/kernel.cuh:18-203 (tile loop, last → first), TFA/mma/softmax.cuh:67-131
 // (online softmax, base-2 exponent, scale = log2e/√hd), TFA/mma/layout.cuh:88-97 (P rounded to bf16 before P·V),
