@@ -400,6 +400,33 @@ def measure_extra_model(name, world, rank, dev, d: Dist, steps, tp_mode):
     return out
 
 
+def measure_batched_decode(spec, w, dev, hbm_peak):
+    """generateSync's batch (the reference CLI feeds four prompts; B ≤ 8 here): B sequences per step, the weights streamed
+    once per step (csrc/gemv_batch.cu, tensor cores).  µs per step and aggregate tokens/s at B = 4 and 8, same prompt
+    length and context as the headline, inputs resident."""
+    import torch
+    from tinygpt_b200 import engine
+    out = {"model": spec.name, "workload": f"{spec.name} bf16, B sequences decoded together after {PROMPT_LEN}-token prompts",
+           "unit": "tokens/s"}
+    eng = engine.DecodeEngine(spec, w)
+    for B in (4, 8):
+        prompts = torch.randint(0, spec.vocab, (B, PROMPT_LEN), generator=torch.Generator().manual_seed(B)).to(dev)
+        eng.reset_cache()
+        eng.gen_next_token(prompts)
+        eng.decode(8)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.decode(NEW_TOKENS - 9)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / (NEW_TOKENS - 9) * 1e3
+        out[f"batch_{B}"] = {"value": B / us * 1e6, "us_per_step": us, "launches_per_step": eng.launches_per_token,
+                             "hbm_frac_of_one_weight_pass": eng.bytes_per_token(PROMPT_LEN + NEW_TOKENS // 2) / (us * 1e-6) / 1e9 / hbm_peak}
+    eng.close()
+    return out
+
+
 def measure_prefill_config(dev, steps=2):
     """BASELINE config 4: Qwen3-1.7B, prefill of 2 048 prompt tokens (tcgen05 GEMMs + tensor-core causal attention) and
     256 decode steps at ctx 2 048 → 2 304.  Prefill against the measured cuBLAS bf16 peak, decode against HBM."""
@@ -513,6 +540,7 @@ def run_ours(args):
         if world == 1:
             others.append(measure_extra_model("Llama-3.2-3B", world, rank, dev, d, 3, tp_mode))
             others.append(measure_prefill_config(dev))
+            others.append(measure_batched_decode(spec, w, dev, measured_peaks()[0]))
         elif tp_mode:
             for name in ("Llama-3.2-3B", "Mistral-7B-v0.3"):
                 others.append(measure_extra_model(name, world, rank, dev, d, 3, tp_mode))
