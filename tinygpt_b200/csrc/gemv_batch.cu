@@ -77,6 +77,18 @@ gemv_batch_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap) 
   const int my_rbs = (p.rowblocks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[0] = global_timer_ns();   // B200_TRACE=1
+  // The RMSNorm weight does not depend on the producer kernel: its loads (k ≤ 4096 stays in registers) are issued
+  // first, before the dependency wait (like gemv_stream_kernel).
+  constexpr int kMaxHoist = 2;
+  uint4 wn[kMaxHoist];
+  if constexpr (PRO == PRO_RMSNORM) {
+    const uint4* wg = reinterpret_cast<const uint4*>(p.norm_w);
+#pragma unroll
+    for (int j = 0; j < kMaxHoist; ++j) {
+      const int i = (int)threadIdx.x + j * kConsumers;
+      wn[j] = (warp < kNW && i < (p.k >> 3)) ? wg[i] : make_uint4(0, 0, 0, 0);
+    }
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full[s], 1);
@@ -115,18 +127,6 @@ gemv_batch_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap) 
   // -------------------------------------------------------------------- consumers
   const int ctid = threadIdx.x;
   const int nvec = p.k >> 3, nvec_pad = p.k_pad >> 3;
-  // what does not depend on the producer kernel is fetched BEFORE griddepcontrol.wait: the RMSNorm weight (k ≤ 4096
-  // stays in registers, like gemv_stream_kernel) — otherwise its (cold, DRAM) load sits between the two barriers
-  constexpr int kMaxHoist = 2;
-  uint4 wn[kMaxHoist];
-  if constexpr (PRO == PRO_RMSNORM) {
-    const uint4* wg = reinterpret_cast<const uint4*>(p.norm_w);
-#pragma unroll
-    for (int j = 0; j < kMaxHoist; ++j) {
-      const int i = ctid + j * kConsumers;
-      wn[j] = (i < nvec) ? wg[i] : make_uint4(0, 0, 0, 0);
-    }
-  }
   pdl_wait();   // the producer kernel's output (x, residual) is complete and visible from here on
   const bool tracing = p.trace != nullptr && blockIdx.x == 0 && ctid == 0;
   long long c0 = 0;
@@ -151,11 +151,14 @@ gemv_batch_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap) 
         if (b < nb) reinterpret_cast<uint4*>(xs + (size_t)b * xstride)[i] = q[b];
     }
   } else {
-    // RMSNorm, one WARP per sequence: lane-strided loads (several in flight), sum of squares by shuffle only, no
-    // cross-warp reduction; the norm weight goes through shared memory (fetched before the dependency wait).  Compact
-    // code on purpose: an 8-way unrolled per-sequence prologue measured 2.4 µs slower per kernel than its instruction
-    // count explains (profiles/r02_trace_batch_prologue.log).  The partition of the sum of squares differs from the
-    // batch-1 kernel's, which is inside the summation-order tolerance this kernel already has.
+    // RMSNorm, one WARP per sequence: lane-strided loads, sum of squares by shuffle only, no cross-warp reduction; the
+    // norm weight goes through shared memory.  The partition of the sum of squares differs from the batch-1 kernel's,
+    // which is inside the summation-order tolerance this kernel already has.
+    // OPEN (profiles/r02_trace_batch_prologue.log): this prologue takes 2.5-2.7 µs per kernel against 0.8 µs at batch 1
+    // and 0.65 µs for the plain staging above.  Ruled out by measurement: the norm-weight load (hoisting it above the
+    // wait or above the first barrier, L2 evict_last, a copy on hot pages — no change).  Not yet tried: the x loop
+    // below runs as ≤ 4 dependent load → use iterations per lane when k/8/32 < 8 (the unroll-by-8 body never executes
+    // and the remainder loop is serial) — batching those loads explicitly is the next experiment.
     uint4* const wv = reinterpret_cast<uint4*>(wns);
     for (int b = warp; b < nb; b += kNW) {
       const uint4* xg = reinterpret_cast<const uint4*>(p.x + (size_t)b * p.x_stride);
