@@ -67,7 +67,7 @@ gemv_batch_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap) 
   __nv_bfloat16* const xs = reinterpret_cast<__nv_bfloat16*>(smem + (size_t)p.stages * kStageBytes);   // [nb][xstride]
   uint64_t* const full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xs) + (size_t)nb * xstride * 2);
   uint64_t* const empty = full + p.stages;
-  float* const red = reinterpret_cast<float*>(empty + p.stages);                                          // [8][kNW]
+  float* const red = reinterpret_cast<float*>(empty + p.stages);               // red[b] = 1/rms of sequence b (64 floats reserved)
   float* const tiles = red + kMaxBatch * kNW;                                                              // [kNW][MT][16][8]
   __nv_bfloat16* const wns = reinterpret_cast<__nv_bfloat16*>(tiles + kNW * MT * 16 * 8);   // RMSNorm weight [k_pad] (PRO_RMSNORM)
 
