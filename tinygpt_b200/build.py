@@ -29,7 +29,7 @@ NVCC_FLAGS = [
     "--expt-relaxed-constexpr",
     "-Xcompiler", "-fPIC,-fno-exceptions,-fvisibility=hidden",
     "-Xptxas", "-v",
-    *os.environ.get("B200_NVCC_EXTRA", "").split(),   # e.g. -DB200_DIAG_PROLOGUE (diagnostic stamps, tools/trace_decode.py)
+    *os.environ.get("B200_NVCC_EXTRA", "").split(),   # extra -D… for one-off diagnostic builds (part of the build digest)
 ]
 
 
