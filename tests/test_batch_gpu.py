@@ -160,7 +160,7 @@ def test_batched_decode_full_size_and_weight_passes(built_lib):
     print(f"[Qwen2.5-0.5B] batched step (B = {B}): {us_b:.1f} us = {B / us_b * 1e6:.0f} tok/s; batch-1 step: {us_1:.1f} us = "
           f"{1 / us_1 * 1e6:.0f} tok/s; {B} sequential batch-1 engines would take {B * us_1:.1f} us")
     # measured: ~1.4 × a batch-1 step at B = 4 (the per-kernel dependency latency of the small model does not shrink)
-    assert us_b < 0.45 * B * us_1
+    assert us_b < 0.5 * B * us_1
     one.close()
     eng.close()
 
