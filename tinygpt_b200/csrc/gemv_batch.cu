@@ -156,9 +156,10 @@ gemv_batch_kernel(const GemvParams p, const __grid_constant__ CUtensorMap tmap) 
     // which is inside the summation-order tolerance this kernel already has.
     // OPEN (profiles/r02_trace_batch_prologue.log): this prologue takes 2.5-2.7 µs per kernel against 0.8 µs at batch 1
     // and 0.65 µs for the plain staging above.  Ruled out by measurement: the norm-weight load (hoisting it above the
-    // wait or above the first barrier, L2 evict_last, a copy on hot pages — no change).  Not yet tried: the x loop
-    // below runs as ≤ 4 dependent load → use iterations per lane when k/8/32 < 8 (the unroll-by-8 body never executes
-    // and the remainder loop is serial) — batching those loads explicitly is the next experiment.
+    // wait or above the first barrier, L2 evict_last, a copy on hot pages — no change).  Diagnosis from the stamps: with
+    // k/8/32 < 8 the unroll-by-8 body of the x loop below never executes and the remainder loop runs its 3-4
+    // iterations as dependent load → use round trips (~0.4 µs each).  Issuing the lane's loads together is the next
+    // change; it was not made because it could not be validated on hardware any more this round.
     uint4* const wv = reinterpret_cast<uint4*>(wns);
     for (int b = warp; b < nb; b += kNW) {
       const uint4* xg = reinterpret_cast<const uint4*>(p.x + (size_t)b * p.x_stride);
